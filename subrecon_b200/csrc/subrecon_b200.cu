@@ -1,0 +1,732 @@
+// subrecon_b200.cu — host side of libsubrecon_b200.so: context, pruning-schedule builder, launch
+// pipeline and the C ABI declared in include/subrecon_b200.h. No torch types, no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/subrecon_b200.h"
+#include "kernels.cuh"
+
+using namespace srk;
+
+static_assert(sizeof(sr_compact) == sizeof(CompactRec), "sr_compact layout");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + (bytes >> 3);          // a little headroom so growing chunk sizes do not thrash
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct EvPair { cudaEvent_t a, b; int kind; int64_t cols; };
+
+}  // namespace
+
+struct sr_ctx {
+    int device = 0;
+    int n_sm = 0;
+    int max_smem = 0;
+    std::string err;
+    cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+
+    // model / rates
+    bool has_model = false, has_rates = false, has_tree = false, has_aln = false;
+    double eval[20], evec[400], ievc[400], pi[20];
+    int K = 0;
+    std::vector<double> rates;
+
+    // tree + schedule
+    int32_t n_nodes = 0, root = 0;
+    std::vector<int32_t> child_off, child_idx, leaf_row;
+    std::vector<double> blen;
+    std::vector<int32_t> ops;           // schedule
+    std::vector<double> op_blen;
+    std::vector<int32_t> node_op;       // node -> op index that applies its parent edge (-1: none)
+    int need_depth = 0;
+    int64_t e_int = 0, e_leaf = 0;
+    int32_t max_leaf_row = -1;
+    double root_blen = 0.0;
+    bool sched_dirty = true, p_dirty = true;
+
+    // options
+    int tile_m = 2;
+    int64_t chunk_cols = 1 << 20;
+    int rescale_every = 8;
+    bool profile = false;
+
+    // device state
+    DevBuf d_model, d_rates, d_ops, d_opblen, d_pstream, d_proot, d_states, d_rootpart, d_rootexp, d_spill;
+    DevBuf d_chunk_states[2], d_chunk_lnl[2], d_chunk_joint[2], d_chunk_compact[2], d_peak;
+    int32_t aln_taxa = 0;
+    int64_t aln_sites = 0, aln_pitch = 0;
+
+    // pinned bounce buffers for pageable caller memory
+    void* h_bounce[2] = {nullptr, nullptr};
+    size_t h_bounce_cap[2] = {0, 0};
+
+    std::vector<EvPair> events;
+    sr_profile prof{};
+};
+
+namespace {
+
+int fail(sr_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            cudaGetLastError();                                                                      \
+            return fail(ctx, _e == cudaErrorMemoryAllocation ? SR_ERR_OOM : SR_ERR_CUDA,             \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                            \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Pruning schedule. The reference recurses (JointBranchReconstruction.java:191-247); here the tree is
+// flattened once into a linear list of steps for a one-register-set + stack machine:
+//   children of a node are visited internal-first, ordered by descending stack need (Strahler order),
+//   so a binary tree of N tips needs at most ceil(log2 N) stacked partials and a caterpillar none.
+// Every step applies exactly one edge (one transition matrix), so step i consumes slot i of the
+// per-rate matrix stream.
+// ------------------------------------------------------------------------------------------------
+int build_schedule(sr_ctx* c) {
+    const int n = c->n_nodes;
+    const auto& off = c->child_off;
+    const auto& idx = c->child_idx;
+    auto is_leaf = [&](int v) { return off[v] == off[v + 1]; };
+    const int rc0 = idx[off[c->root]], rc1 = idx[off[c->root] + 1];
+
+    // post-order over the whole tree (iterative) to compute the stack need of every internal node
+    std::vector<int> order;
+    order.reserve(n);
+    {
+        std::vector<int> st{c->root};
+        while (!st.empty()) {
+            int v = st.back(); st.pop_back();
+            order.push_back(v);
+            for (int e = off[v]; e < off[v + 1]; ++e) st.push_back(idx[e]);
+        }
+    }
+    if ((int)order.size() != n) return fail(c, SR_ERR_ARG, "tree is not connected: %d of %d nodes reachable from the root", (int)order.size(), n);
+    std::vector<int> need(n, 0);
+    std::vector<int32_t> ord(idx.size());      // per node: children reordered (internal by need desc, then tips)
+    for (int oi = n - 1; oi >= 0; --oi) {
+        const int v = order[oi];
+        if (is_leaf(v)) continue;
+        std::vector<int> inner, tips;
+        for (int e = off[v]; e < off[v + 1]; ++e) (is_leaf(idx[e]) ? tips : inner).push_back(idx[e]);
+        std::stable_sort(inner.begin(), inner.end(), [&](int a, int b) { return need[a] > need[b]; });
+        int nd = 0;
+        for (size_t i = 0; i < inner.size(); ++i) nd = std::max(nd, need[inner[i]] + (i > 0 ? 1 : 0));
+        need[v] = nd;
+        int e = off[v];
+        for (int x : inner) ord[e++] = x;
+        for (int x : tips) ord[e++] = x;
+    }
+
+    c->ops.clear();
+    c->op_blen.clear();
+    c->node_op.assign(n, -1);
+    c->e_int = c->e_leaf = 0;
+    c->max_leaf_row = -1;
+    const int T = std::max(1, c->rescale_every);
+    int s_cur = 0;                               // edges multiplied into A since its last rescale
+    std::vector<int> s_stack;
+
+    auto emit = [&](int code, int child, bool identity) {
+        int32_t w = code;
+        if (code <= OP_LEAF_MUL) {
+            w |= (int32_t)((uint32_t)c->leaf_row[child] << OP_ROW_SHIFT);
+            c->max_leaf_row = std::max(c->max_leaf_row, c->leaf_row[child]);
+        }
+        if (identity) w |= OPF_IDENTITY;
+        c->ops.push_back(w);
+        c->op_blen.push_back(c->blen[child]);
+        c->node_op[child] = (int)c->ops.size() - 1;
+        if (!identity) { if (code <= OP_LEAF_MUL) ++c->e_leaf; else ++c->e_int; }
+        if (code == OP_LEAF_SET) s_cur = 1;
+        else if (code == OP_MV_MULPOP) { s_cur += 1 + s_stack.back(); s_stack.pop_back(); }
+        else s_cur += 1;
+        if (s_cur >= T) { c->ops.back() |= OPF_RESCALE; s_cur = 0; }
+    };
+
+    struct Frame { int v; int i; };              // i = next position in ord[] of v
+    for (int which = 0; which < 2; ++which) {
+        const int r = which == 0 ? rc0 : rc1;
+        if (is_leaf(r)) {
+            emit(OP_LEAF_SET, r, /*identity=*/true);
+        } else {
+            std::vector<Frame> fr{{r, 0}};
+            while (!fr.empty()) {
+                Frame& f = fr.back();
+                const int v = f.v, deg = off[v + 1] - off[v];
+                if (f.i == deg) {                          // node complete: hand the partial to the parent
+                    fr.pop_back();
+                    if (!fr.empty()) {
+                        Frame& pf = fr.back();
+                        const bool first = (pf.i == 1);    // v was ord[0] of its parent
+                        emit(first ? OP_MV_SET : OP_MV_MULPOP, v, false);
+                    }
+                    continue;
+                }
+                const int ch = ord[off[v] + f.i];
+                if (!is_leaf(ch)) {
+                    if (f.i > 0) { c->ops.back() |= OPF_PUSH; s_stack.push_back(s_cur); }
+                    ++f.i;
+                    fr.push_back({ch, 0});
+                } else {
+                    emit(f.i == 0 ? OP_LEAF_SET : OP_LEAF_MUL, ch, false);
+                    ++f.i;
+                }
+            }
+        }
+        c->ops.back() |= (which == 0 ? OPF_STORE_A : OPF_STORE_B);
+    }
+    c->need_depth = std::max(is_leaf(rc0) ? 0 : need[rc0], is_leaf(rc1) ? 0 : need[rc1]);
+    c->root_blen = c->blen[rc0] + c->blen[rc1];
+    c->sched_dirty = false;
+    c->p_dirty = true;
+    return SR_OK;
+}
+
+void prof_begin(sr_ctx* c, cudaStream_t s, int kind, int64_t cols) {
+    if (!c->profile) return;
+    EvPair e{};
+    e.kind = kind; e.cols = cols;
+    cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, s);
+    c->events.push_back(e);
+}
+void prof_end(sr_ctx* c, cudaStream_t s) {
+    if (!c->profile) return;
+    cudaEventRecord(c->events.back().b, s);
+}
+
+// Upload schedule + model, run K1 when anything it depends on changed.
+int ensure_pstream(sr_ctx* c, cudaStream_t s) {
+    if (!c->has_model || !c->has_rates || !c->has_tree)
+        return fail(c, SR_ERR_STATE, "model, rates and tree must be set before running");
+    if (c->sched_dirty) { int rc = build_schedule(c); if (rc) return rc; }
+    if (!c->p_dirty) return SR_OK;
+    const int n_ops = (int)c->ops.size();
+    CUDA_TRY(c, c->d_model.reserve(sizeof(double) * 840));
+    CUDA_TRY(c, c->d_rates.reserve(sizeof(double) * c->K));
+    CUDA_TRY(c, c->d_ops.reserve(sizeof(int32_t) * n_ops));
+    CUDA_TRY(c, c->d_opblen.reserve(sizeof(double) * n_ops));
+    CUDA_TRY(c, c->d_pstream.reserve(sizeof(double) * (size_t)c->K * n_ops * SLOT_DOUBLES));
+    CUDA_TRY(c, c->d_proot.reserve(sizeof(double) * (size_t)c->K * 400));
+    double hm[840];
+    memcpy(hm, c->eval, 160); memcpy(hm + 20, c->evec, 3200); memcpy(hm + 420, c->ievc, 3200); memcpy(hm + 820, c->pi, 160);
+    // plain synchronous copies: these are tiny, and the staging arrays live on this stack frame
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    CUDA_TRY(c, cudaMemcpy(c->d_model.p, hm, sizeof(hm), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_rates.p, c->rates.data(), sizeof(double) * c->K, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_ops.p, c->ops.data(), sizeof(int32_t) * n_ops, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_opblen.p, c->op_blen.data(), sizeof(double) * n_ops, cudaMemcpyHostToDevice));
+    PBuildParams pp{};
+    pp.eval = c->d_model.as<double>();
+    pp.evec = pp.eval + 20;
+    pp.ievc = pp.eval + 420;
+    pp.rates = c->d_rates.as<double>();
+    pp.ops = c->d_ops.as<int32_t>();
+    pp.op_blen = c->d_opblen.as<double>();
+    pp.pstream = c->d_pstream.as<double>();
+    pp.proot = c->d_proot.as<double>();
+    pp.root_blen = c->root_blen;
+    pp.n_ops = n_ops;
+    pp.K = c->K;
+    prof_begin(c, s, 0, 0);
+    pbuild_kernel<<<dim3(n_ops + 1, c->K), 128, 0, s>>>(pp);
+    prof_end(c, s);
+    CUDA_TRY(c, cudaGetLastError());
+    c->p_dirty = false;
+    return SR_OK;
+}
+
+template <int M, int NSTAGE>
+int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
+    using Cfg = PruneCfg<M>;
+    const int fixed = NSTAGE * STAGE_BYTES + prune_bar_bytes(NSTAGE);
+    int levels = (c->max_smem - fixed) / Cfg::LEVEL_BYTES;
+    levels = std::max(0, std::min(levels, c->need_depth));
+    const int spill_levels = c->need_depth - levels;
+    const int n_items = p.n_tiles * p.K;
+    const int grid = std::min(n_items, c->n_sm);
+    if (spill_levels > 0)
+        CUDA_TRY(c, c->d_spill.reserve((size_t)grid * spill_levels * Cfg::LEVEL_BYTES));
+    p.smem_levels = levels;
+    p.spill_levels = spill_levels;
+    p.spill = c->d_spill.as<double>();
+    const int smem = fixed + levels * Cfg::LEVEL_BYTES;
+    auto kern = prune_kernel<M, NSTAGE>;
+    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    prof_begin(c, s, 1, cols);
+    kern<<<grid, PRUNE_THREADS, smem, s>>>(p);
+    prof_end(c, s);
+    CUDA_TRY(c, cudaGetLastError());
+    return SR_OK;
+}
+
+// Columns [col_begin, col_begin+n) of a device block of states -> outputs (device pointers) at out0.
+int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch, int64_t col_begin, int64_t n,
+              double* d_lnl, double* d_joint, void* d_compact, double threshold, int64_t out0) {
+    if (n <= 0) return SR_OK;
+    int rc = ensure_pstream(c, s);
+    if (rc) return rc;
+    const int S = (c->tile_m == 4) ? PruneCfg<4>::S : PruneCfg<2>::S;
+    const int64_t col_start = (col_begin / 16) * 16;
+    const int64_t skip = col_begin - col_start;
+    const int64_t tiles = (skip + n + S - 1) / S;
+    if (tiles > INT32_MAX / std::max(1, c->K)) return fail(c, SR_ERR_ARG, "too many columns in one launch; lower chunk_cols");
+    const int64_t ncp = tiles * S;
+    CUDA_TRY(c, c->d_rootpart.reserve(sizeof(double) * 2 * (size_t)c->K * ncp * NS));
+    CUDA_TRY(c, c->d_rootexp.reserve(sizeof(int32_t) * (size_t)c->K * ncp));
+    PruneParams p{};
+    p.ops = c->d_ops.as<int32_t>();
+    p.pstream = c->d_pstream.as<double>();
+    p.states = d_states;
+    p.pitch = pitch;
+    p.col0 = col_start;
+    p.rootpart = c->d_rootpart.as<double>();
+    p.rootexp = c->d_rootexp.as<int32_t>();
+    p.ncp = ncp;
+    p.n_ops = (int)c->ops.size();
+    p.n_tiles = (int)tiles;
+    p.K = c->K;
+    rc = (c->tile_m == 4) ? launch_prune<4, 6>(c, s, p, n) : launch_prune<2, 8>(c, s, p, n);
+    if (rc) return rc;
+    RootParams r{};
+    r.rootpart = p.rootpart;
+    r.rootexp = p.rootexp;
+    r.proot = c->d_proot.as<double>();
+    r.pi = c->d_model.as<double>() + 820;
+    r.lnl = d_lnl;
+    r.joint = d_joint;
+    r.compact = d_compact;
+    r.threshold = threshold;
+    r.ncp = ncp;
+    r.n = n;
+    r.col_skip = skip;
+    r.out0 = out0;
+    r.K = c->K;
+    const int64_t blocks = std::min<int64_t>((n + ROOT_WARPS - 1) / ROOT_WARPS, (int64_t)c->n_sm * 8);
+    prof_begin(c, s, 2, n);
+    root_kernel<<<(unsigned)blocks, ROOT_WARPS * 32, 0, s>>>(r);
+    prof_end(c, s);
+    CUDA_TRY(c, cudaGetLastError());
+    return SR_OK;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int check_run_args(sr_ctx* c, int64_t site0, int64_t n, int64_t n_sites, const void* lnl) {
+    if (!c) return SR_ERR_ARG;
+    if (site0 < 0 || n < 0 || site0 + n > n_sites)
+        return fail(c, SR_ERR_ARG, "column range [%lld, %lld) outside the alignment (%lld sites)", (long long)site0,
+                    (long long)(site0 + n), (long long)n_sites);
+    if (n > 0 && !lnl) return fail(c, SR_ERR_ARG, "lnl output is required");
+    return SR_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ ABI
+extern "C" {
+
+int sr_create(sr_ctx** out, int device) {
+    if (!out) return fail(nullptr, SR_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SR_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n_dev) return fail(nullptr, SR_ERR_ARG, "device %d out of range (0..%d)", device, n_dev - 1);
+    sr_ctx* c = new (std::nothrow) sr_ctx();
+    if (!c) return fail(nullptr, SR_ERR_OOM, "out of host memory");
+    c->device = device;
+    cudaDeviceProp pr{};
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&pr, device)) != cudaSuccess) {
+        delete c;
+        return fail(nullptr, SR_ERR_CUDA, "cannot open device %d: %s", device, cudaGetErrorString(e));
+    }
+    if (pr.major != 10) {
+        delete c;
+        return fail(nullptr, SR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this build targets sm_100a (B200) only", device, pr.major, pr.minor);
+    }
+    c->n_sm = pr.multiProcessorCount;
+    c->max_smem = (int)pr.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return fail(nullptr, SR_ERR_CUDA, "cannot create CUDA streams");
+    }
+    *out = c;
+    return SR_OK;
+}
+
+void sr_destroy(sr_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (int i = 0; i < 2; ++i) if (c->h_bounce[i]) cudaFreeHost(c->h_bounce[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    delete c;
+}
+
+const char* sr_last_error(const sr_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int sr_set_model(sr_ctx* c, const double* eval, const double* evec, const double* ievc, const double* pi) {
+    if (!c) return SR_ERR_ARG;
+    if (!eval || !evec || !ievc || !pi) return fail(c, SR_ERR_ARG, "NULL model array");
+    for (int i = 0; i < 20; ++i)
+        if (!(pi[i] >= 0.0) || !std::isfinite(eval[i])) return fail(c, SR_ERR_ARG, "pi/eval entry %d is not a finite non-negative number", i);
+    memcpy(c->eval, eval, 160); memcpy(c->evec, evec, 3200); memcpy(c->ievc, ievc, 3200); memcpy(c->pi, pi, 160);
+    c->has_model = true;
+    c->p_dirty = true;
+    return SR_OK;
+}
+
+int sr_set_rates(sr_ctx* c, int K, const double* rates) {
+    if (!c) return SR_ERR_ARG;
+    if (K < 1) return fail(c, SR_ERR_ARG, "ERROR: -n (number of rate categories) must be 1 or higher");   // SubRecon.java:209-210
+    if (!rates) return fail(c, SR_ERR_ARG, "rates is NULL");
+    for (int i = 0; i < K; ++i)
+        if (!std::isfinite(rates[i]) || rates[i] < 0.0) return fail(c, SR_ERR_ARG, "rate %d is not a finite non-negative number", i);
+    c->K = K;
+    c->rates.assign(rates, rates + K);
+    c->has_rates = true;
+    c->p_dirty = true;
+    return SR_OK;
+}
+
+int sr_set_tree(sr_ctx* c, int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                const int32_t* leaf_row, int32_t root) {
+    if (!c) return SR_ERR_ARG;
+    if (n_nodes < 3 || !child_off || !child_idx || !blen || !leaf_row) return fail(c, SR_ERR_ARG, "bad tree arrays");
+    if (root < 0 || root >= n_nodes) return fail(c, SR_ERR_ARG, "root index out of range");
+    if (child_off[0] != 0) return fail(c, SR_ERR_ARG, "child_off[0] must be 0");
+    for (int v = 0; v < n_nodes; ++v) {
+        const int deg = child_off[v + 1] - child_off[v];
+        if (deg < 0) return fail(c, SR_ERR_ARG, "child_off is not monotone at node %d", v);
+        if (deg == 1) return fail(c, SR_ERR_ARG, "Node with single child enountered (node %d)", v);   // PAL ReadTree::readNH
+        if (deg == 0 && leaf_row[v] < 0) return fail(c, SR_ERR_ARG, "tip node %d has no alignment row (taxon missing from the alignment)", v);
+        if (deg == 0 && leaf_row[v] >= (1 << 23)) return fail(c, SR_ERR_UNSUPPORTED, "alignment row %d exceeds 2^23", leaf_row[v]);
+        if (!(blen[v] >= 0.0) && v != root) return fail(c, SR_ERR_ARG, "branch length of node %d is negative or NaN", v);
+    }
+    const int n_edges = child_off[n_nodes];
+    if (n_edges != n_nodes - 1) return fail(c, SR_ERR_ARG, "tree has %d edges for %d nodes", n_edges, n_nodes);
+    for (int e = 0; e < n_edges; ++e)
+        if (child_idx[e] < 0 || child_idx[e] >= n_nodes || child_idx[e] == root) return fail(c, SR_ERR_ARG, "child_idx[%d] invalid", e);
+    if (child_off[root + 1] - child_off[root] != 2)
+        return fail(c, SR_ERR_ARG, "ERROR: Tree root has more than two descendents. Is the tree rooted correctly?");   // SubRecon.java:212-213
+    c->n_nodes = n_nodes;
+    c->root = root;
+    c->child_off.assign(child_off, child_off + n_nodes + 1);
+    c->child_idx.assign(child_idx, child_idx + n_edges);
+    c->blen.assign(blen, blen + n_nodes);
+    c->leaf_row.assign(leaf_row, leaf_row + n_nodes);
+    c->has_tree = true;
+    c->sched_dirty = true;
+    return build_schedule(c);
+}
+
+int sr_set_alignment(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* states, int64_t pitch) {
+    if (!c) return SR_ERR_ARG;
+    if (n_taxa < 1 || n_sites < 0 || !states || pitch < n_sites) return fail(c, SR_ERR_ARG, "bad alignment arguments");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int64_t dp = ((n_sites + 255) / 256) * 256 + 256;       // row pitch: 16-byte aligned rows + slack for the last tile
+    CUDA_TRY(c, c->d_states.reserve((size_t)dp * n_taxa + 512));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemset(c->d_states.p, SR_STATE_MISSING, (size_t)dp * n_taxa + 512));
+    if (n_sites > 0)
+        CUDA_TRY(c, cudaMemcpy2D(c->d_states.p, dp, states, pitch, n_sites, n_taxa, cudaMemcpyHostToDevice));
+    c->aln_taxa = n_taxa;
+    c->aln_sites = n_sites;
+    c->aln_pitch = dp;
+    c->has_aln = true;
+    return SR_OK;
+}
+
+int sr_run_device(sr_ctx* c, int64_t site0, int64_t n, double* d_lnl, double* d_joint, sr_compact* d_compact,
+                  double threshold, void* stream) {
+    if (!c) return SR_ERR_ARG;
+    if (!c->has_aln) return fail(c, SR_ERR_STATE, "alignment not set");
+    int rc = check_run_args(c, site0, n, c->aln_sites, d_lnl ? (void*)d_lnl : (void*)d_joint);
+    if (rc) return rc;
+    if (c->has_tree && c->max_leaf_row >= c->aln_taxa) return fail(c, SR_ERR_ARG, "tree refers to alignment row %d but the alignment has %d taxa", c->max_leaf_row, c->aln_taxa);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    for (int64_t done = 0; done < n;) {
+        const int64_t m = std::min(n - done, c->chunk_cols);
+        rc = run_block(c, s, c->d_states.as<uint8_t>(), c->aln_pitch, site0 + done, m, d_lnl, d_joint, d_compact, threshold, done);
+        if (rc) return rc;
+        done += m;
+    }
+    return SR_OK;
+}
+
+static int d2h(sr_ctx* c, cudaStream_t s, void* dst, const void* src, size_t bytes) {
+    CUDA_TRY(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    return SR_OK;
+}
+
+int sr_run(sr_ctx* c, int64_t site0, int64_t n, double* lnl, double* joint, sr_compact* compact, double threshold) {
+    if (!c) return SR_ERR_ARG;
+    if (!c->has_aln) return fail(c, SR_ERR_STATE, "alignment not set");
+    int rc = check_run_args(c, site0, n, c->aln_sites, lnl);
+    if (rc) return rc;
+    if (c->has_tree && c->max_leaf_row >= c->aln_taxa) return fail(c, SR_ERR_ARG, "tree refers to alignment row %d but the alignment has %d taxa", c->max_leaf_row, c->aln_taxa);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    // chunked: compute chunk i on `stream` while chunk i-1 drains to the host on `s_d2h`
+    const int64_t chunk = std::min<int64_t>(c->chunk_cols, std::max<int64_t>(n, 1));
+    cudaEvent_t done_ev[2], free_ev[2];
+    for (int i = 0; i < 2; ++i) { CUDA_TRY(c, cudaEventCreateWithFlags(&done_ev[i], cudaEventDisableTiming)); CUDA_TRY(c, cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming)); }
+    int ci = 0;
+    rc = SR_OK;
+    for (int64_t done = 0; done < n && rc == SR_OK; ++ci) {
+        const int b = ci & 1;
+        const int64_t m = std::min(n - done, chunk);
+        if ((rc = (c->d_chunk_lnl[b].reserve(sizeof(double) * m) == cudaSuccess ? SR_OK : fail(c, SR_ERR_OOM, "device OOM (lnl chunk)")))) break;
+        if (joint && c->d_chunk_joint[b].reserve(sizeof(double) * 400 * m) != cudaSuccess) { rc = fail(c, SR_ERR_OOM, "device OOM (joint chunk)"); break; }
+        if (compact && c->d_chunk_compact[b].reserve(sizeof(sr_compact) * m) != cudaSuccess) { rc = fail(c, SR_ERR_OOM, "device OOM (compact chunk)"); break; }
+        if (ci >= 2) cudaStreamWaitEvent(c->stream, free_ev[b], 0);      // buffer b drained?
+        rc = run_block(c, c->stream, c->d_states.as<uint8_t>(), c->aln_pitch, site0 + done, m, c->d_chunk_lnl[b].as<double>(),
+                       joint ? c->d_chunk_joint[b].as<double>() : nullptr, compact ? c->d_chunk_compact[b].p : nullptr, threshold, 0);
+        if (rc) break;
+        cudaEventRecord(done_ev[b], c->stream);
+        cudaStreamWaitEvent(c->s_d2h, done_ev[b], 0);
+        if ((rc = d2h(c, c->s_d2h, lnl + done, c->d_chunk_lnl[b].p, sizeof(double) * m))) break;
+        if (joint && (rc = d2h(c, c->s_d2h, joint + done * 400, c->d_chunk_joint[b].p, sizeof(double) * 400 * m))) break;
+        if (compact && (rc = d2h(c, c->s_d2h, compact + done, c->d_chunk_compact[b].p, sizeof(sr_compact) * m))) break;
+        cudaEventRecord(free_ev[b], c->s_d2h);
+        done += m;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_d2h);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(done_ev[i]); cudaEventDestroy(free_ev[i]); }
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, SR_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    }
+    return SR_OK;
+}
+
+int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* states, int64_t pitch, int64_t site0,
+                    int64_t n, double* lnl, double* joint, sr_compact* compact, double threshold) {
+    if (!c) return SR_ERR_ARG;
+    if (n_taxa < 1 || !states || pitch < n_sites) return fail(c, SR_ERR_ARG, "bad alignment arguments");
+    int rc = check_run_args(c, site0, n, n_sites, lnl);
+    if (rc) return rc;
+    if (c->has_tree && c->max_leaf_row >= n_taxa) return fail(c, SR_ERR_ARG, "tree refers to alignment row %d but the alignment has %d taxa", c->max_leaf_row, n_taxa);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    rc = ensure_pstream(c, c->stream);
+    if (rc) return rc;
+    // three-stage pipeline over column chunks: H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h), two buffers each
+    const int64_t chunk = std::max<int64_t>(256, (std::min<int64_t>(c->chunk_cols, std::max<int64_t>(n, 1)) + 255) / 256 * 256);
+    const int64_t cpitch = chunk + 256;
+    cudaEvent_t up_ev[2], done_ev[2], free_ev[2], sfree_ev[2];
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(c, cudaEventCreateWithFlags(&up_ev[i], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&done_ev[i], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&sfree_ev[i], cudaEventDisableTiming));
+    }
+    int ci = 0;
+    for (int64_t done = 0; done < n && rc == SR_OK; ++ci) {
+        const int b = ci & 1;
+        const int64_t m = std::min(n - done, chunk);
+        if (c->d_chunk_states[b].reserve((size_t)cpitch * n_taxa + 512) != cudaSuccess ||
+            c->d_chunk_lnl[b].reserve(sizeof(double) * m) != cudaSuccess ||
+            (joint && c->d_chunk_joint[b].reserve(sizeof(double) * 400 * m) != cudaSuccess) ||
+            (compact && c->d_chunk_compact[b].reserve(sizeof(sr_compact) * m) != cudaSuccess)) {
+            cudaGetLastError();
+            rc = fail(c, SR_ERR_OOM, "device OOM (pipeline chunk buffers)");
+            break;
+        }
+        if (ci >= 2) cudaStreamWaitEvent(c->s_h2d, sfree_ev[b], 0);     // kernels of chunk ci-2 have consumed states buffer b
+        cudaError_t e = cudaMemcpy2DAsync(c->d_chunk_states[b].p, cpitch, states + site0 + done, pitch, m, n_taxa, cudaMemcpyHostToDevice, c->s_h2d);
+        if (e != cudaSuccess) { rc = fail(c, SR_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+        cudaEventRecord(up_ev[b], c->s_h2d);
+        cudaStreamWaitEvent(c->stream, up_ev[b], 0);
+        if (ci >= 2) cudaStreamWaitEvent(c->stream, free_ev[b], 0);     // output buffers b drained
+        rc = run_block(c, c->stream, c->d_chunk_states[b].as<uint8_t>(), cpitch, 0, m, c->d_chunk_lnl[b].as<double>(),
+                       joint ? c->d_chunk_joint[b].as<double>() : nullptr, compact ? c->d_chunk_compact[b].p : nullptr, threshold, 0);
+        if (rc) break;
+        cudaEventRecord(done_ev[b], c->stream);
+        cudaEventRecord(sfree_ev[b], c->stream);
+        cudaStreamWaitEvent(c->s_d2h, done_ev[b], 0);
+        if ((rc = d2h(c, c->s_d2h, lnl + done, c->d_chunk_lnl[b].p, sizeof(double) * m))) break;
+        if (joint && (rc = d2h(c, c->s_d2h, joint + done * 400, c->d_chunk_joint[b].p, sizeof(double) * 400 * m))) break;
+        if (compact && (rc = d2h(c, c->s_d2h, compact + done, c->d_chunk_compact[b].p, sizeof(sr_compact) * m))) break;
+        cudaEventRecord(free_ev[b], c->s_d2h);
+        done += m;
+    }
+    cudaError_t e0 = cudaStreamSynchronize(c->s_h2d), e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_d2h);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(up_ev[i]); cudaEventDestroy(done_ev[i]); cudaEventDestroy(free_ev[i]); cudaEventDestroy(sfree_ev[i]); }
+    if (rc) return rc;
+    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, SR_ERR_CUDA, "pipeline execution failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2)));
+    }
+    return SR_OK;
+}
+
+void* sr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void sr_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) return SR_ERR_ARG;
+    const std::string k(name);
+    if (k == "tile_m") {
+        if (value != 2 && value != 4) return fail(c, SR_ERR_ARG, "tile_m must be 2 or 4");
+        c->tile_m = (int)value;
+    } else if (k == "chunk_cols") {
+        if (value < 256) return fail(c, SR_ERR_ARG, "chunk_cols must be >= 256");
+        c->chunk_cols = (value + 255) / 256 * 256;
+    } else if (k == "profile") {
+        c->profile = value != 0;
+    } else if (k == "rescale_every") {
+        if (value < 1 || value > 20) return fail(c, SR_ERR_ARG, "rescale_every must be in 1..20");
+        c->rescale_every = (int)value;
+        c->sched_dirty = true;
+    } else {
+        return fail(c, SR_ERR_ARG, "unknown option '%s'", name);
+    }
+    return SR_OK;
+}
+
+int sr_get_profile(sr_ctx* c, sr_profile* out) {
+    if (!c || !out) return SR_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaDeviceSynchronize());
+    for (auto& e : c->events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            if (e.kind == 0) { c->prof.ms_pbuild += ms; ++c->prof.n_pbuild; }
+            else if (e.kind == 1) { c->prof.ms_prune += ms; ++c->prof.n_prune; c->prof.columns_pruned += e.cols; }
+            else { c->prof.ms_root += ms; ++c->prof.n_root; }
+        } else {
+            cudaGetLastError();
+        }
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    c->events.clear();
+    *out = c->prof;
+    return SR_OK;
+}
+
+int sr_profile_reset(sr_ctx* c) {
+    if (!c) return SR_ERR_ARG;
+    sr_profile tmp;
+    int rc = sr_get_profile(c, &tmp);
+    c->prof = sr_profile{};
+    return rc;
+}
+
+int sr_schedule_info(sr_ctx* c, int64_t* n_steps, int32_t* stack_depth, double* flops) {
+    if (!c) return SR_ERR_ARG;
+    if (!c->has_tree) return fail(c, SR_ERR_STATE, "tree not set");
+    if (c->sched_dirty) { int rc = build_schedule(c); if (rc) return rc; }
+    if (n_steps) *n_steps = (int64_t)c->ops.size();
+    if (stack_depth) *stack_depth = c->need_depth;
+    if (flops) *flops = 820.0 * (double)c->e_int + 20.0 * (double)c->e_leaf + 1200.0;
+    return SR_OK;
+}
+
+int sr_measure_fp64_peak(sr_ctx* c, double ms_target, double* tflops) {
+    if (!c || !tflops) return SR_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, c->d_peak.reserve(64));
+    const int blocks = c->n_sm * 4, threads = 256, iters = 2048;
+    const double flop = 2.0 * 256.0 * (double)(blocks * threads / 32) * iters * 4 * 8;
+    cudaEvent_t a, b;
+    CUDA_TRY(c, cudaEventCreate(&a)); CUDA_TRY(c, cudaEventCreate(&b));
+    for (int i = 0; i < 2; ++i) dmma_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->d_peak.as<double>(), iters, 0.5, 0.25);
+    double best = 0.0, spent = 0.0;
+    while (spent < ms_target) {
+        cudaEventRecord(a, c->stream);
+        dmma_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->d_peak.as<double>(), iters, 0.5, 0.25);
+        cudaEventRecord(b, c->stream);
+        cudaError_t e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) { cudaEventDestroy(a); cudaEventDestroy(b); return fail(c, SR_ERR_CUDA, "peak probe failed: %s", cudaGetErrorString(e)); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        spent += ms;
+        best = std::max(best, flop / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *tflops = best;
+    return SR_OK;
+}
+
+int sr_debug_pmatrix(sr_ctx* c, int32_t node, int32_t k, double* out) {
+    if (!c || !out) return SR_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_pstream(c, c->stream);
+    if (rc) return rc;
+    if (k < 0 || k >= c->K || node < 0 || node >= c->n_nodes) return fail(c, SR_ERR_ARG, "node or rate class out of range");
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (node == c->root) {
+        CUDA_TRY(c, cudaMemcpy(out, c->d_proot.as<double>() + (size_t)k * 400, 3200, cudaMemcpyDeviceToHost));
+        return SR_OK;
+    }
+    const int op = c->node_op[node];
+    if (op < 0) return fail(c, SR_ERR_ARG, "node %d has no pruning step", node);
+    double slot[SLOT_DOUBLES];
+    CUDA_TRY(c, cudaMemcpy(slot, c->d_pstream.as<double>() + ((size_t)k * c->ops.size() + op) * SLOT_DOUBLES, SLOT_BYTES, cudaMemcpyDeviceToHost));
+    const int code = c->ops[op] & OP_CODE_MASK;
+    if (code >= OP_MV_SET) {
+        for (int e = 0; e < SLOT_DOUBLES; ++e) {
+            const int lane = e & 31, st = e >> 5, s = st / 3, tt = st % 3, g = lane >> 2, q = lane & 3, r = 2 * tt + (g & 1);
+            if (r < 5) out[(5 * (g >> 1) + r) * 20 + 5 * q + s] = slot[e];
+        }
+    } else {
+        for (int s = 0; s < 20; ++s)
+            for (int i = 0; i < 20; ++i) out[i * 20 + s] = slot[s * 20 + i];
+    }
+    return SR_OK;
+}
+
+}  // extern "C"
