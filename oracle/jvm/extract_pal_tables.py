@@ -14,8 +14,11 @@ import os
 import struct
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from jvm.classfile import Jar  # noqa: E402
+try:
+    from .classfile import Jar
+except ImportError:                                   # run as a script
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle.jvm.classfile import Jar  # noqa: E402
 
 
 def _scan(cf, code):

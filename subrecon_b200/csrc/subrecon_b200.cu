@@ -343,11 +343,6 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
     return SR_OK;
 }
 
-bool is_pinned(const void* p) {
-    cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
-}
 
 int check_run_args(sr_ctx* c, int64_t site0, int64_t n, int64_t n_sites, const void* lnl) {
     if (!c) return SR_ERR_ARG;

@@ -127,7 +127,7 @@ def _incomplete_gamma(x, alpha, lga):
         gin += term
         if not term > accurate:
             break
-    return gin * factor / alpha
+    return gin * (factor / alpha)
 
 
 def _point_normal(prob):
@@ -223,3 +223,15 @@ def host_model(model_id: str, frequencies=None) -> HostModel:
     w, v, iv = eigensystem(R)
     q = np.array([x for row in tab["q_upper_rows"] for x in row])
     return HostModel(key, pi, log_pi, pi_model, q, w, v, iv)
+
+
+def normalise_cli_frequencies(values):
+    """`-pi` handling of cli/CommandArgs.java:91-111: sequential sum, every value divided by it."""
+    vals = [float(v) for v in values]
+    if len(vals) != 20:
+        raise ValueError("Error: if specifying amino acid frequencies, exactly 20 values must be provided "
+                         "and delimited by comma with no spaces")
+    s = 0.0
+    for v in vals:
+        s += v
+    return [v / s for v in vals]

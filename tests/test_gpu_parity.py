@@ -1,0 +1,276 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): site log-likelihoods and all 400 probabilities within 1e-9 relative in FP64
+(entries below 1e-300 compared absolutely). At BASELINE's full sizes the oracle is too slow, so those cases use
+size-independent properties: posteriors sum to 1, results are independent of where a column sits in the batch /
+tile / chunk (bit-identical), streamed == resident, and the compact scan matches numpy on the full matrix.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import load_example, rel_err, synthetic
+from oracle import oracle
+from subrecon_b200 import native, recon, treeio
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = native.Context(0)
+    yield c
+    c.close()
+
+
+def setup(ctx, p, tile_m=2):
+    ctx.set_option("tile_m", tile_m)
+    ctx.set_option("chunk_cols", 1 << 20)
+    ctx.set_model(p.model.Eval, p.model.Evec, p.model.Ievc, p.model.pi)
+    ctx.set_rates(p.rates)
+    ctx.set_tree(p.flat)
+    ctx.set_alignment(p.states)
+
+
+def check(ctx, p, lnl, joint, **kw):
+    r = ctx.run(**kw)
+    assert rel_err(r["lnl"], lnl) < TOL
+    assert rel_err(r["joint"], joint) < TOL
+    assert np.max(np.abs(r["joint"].sum(axis=(1, 2)) - 1.0)) < 1e-12       # checkSumToOne, at 1e-12 not 1e-6
+    return r
+
+
+@pytest.mark.parametrize("tile_m", [2, 4])
+def test_cfg1_lysozyme_vs_oracle_and_golden(ctx, example_problem, tile_m):
+    p = example_problem
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
+    setup(ctx, p, tile_m)
+    r = check(ctx, p, lnl, joint)
+    g = np.load(os.path.join(HERE, "golden", "lysozyme_golden.npz"))       # PAL-bytecode golden
+    assert rel_err(r["lnl"], g["lnl"]) < TOL and rel_err(r["joint"], g["joint"]) < TOL
+    tot = 0.0
+    for x in r["lnl"]:
+        tot += x
+    assert abs(tot - (-673.1980928246)) < 1e-9
+
+
+def test_cfg1_printed_output_identical(ctx, example_problem):
+    """Identical printed output at the default -sd and threshold, and with -threshold 0.0 -verbose."""
+    p = example_problem
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
+    setup(ctx, p)
+    r = ctx.run()
+    for thr, verbose in ((0.5, False), (0.0, True)):
+        want = recon.run_columns([recon.SiteResult(i, lnl[i], joint[i], thr) for i in range(len(lnl))], verbose, thr)
+        got = recon.run_columns([recon.SiteResult(i, r["lnl"][i], r["joint"][i], thr) for i in range(len(lnl))], verbose, thr)
+        assert got[:-1] == want[:-1]                                      # every Result line byte-identical
+        assert abs(float(got[-1].split()[-1]) - float(want[-1].split()[-1])) < 1e-8   # Total lnL compared numerically
+    lines = recon.run_columns([recon.SiteResult(i, r["lnl"][i], r["joint"][i]) for i in range(130)])
+    assert [ln.split("\t")[1] for ln in lines if ln.startswith("Result")] == ["14", "21", "23", "41", "50", "62", "87", "101"]
+
+
+def test_device_built_matrices_match_pal(ctx, example_problem):
+    """K1 against `model.getTransitionProbabilities` (JointBranchReconstruction.java:217)."""
+    p = example_problem
+    setup(ctx, p)
+    worst = 0.0
+    for v in range(1, p.flat.n_nodes):
+        if v in p.tree.children[0]:
+            continue                                                      # root edges are merged (:99)
+        for k in range(len(p.rates)):
+            P = ctx.debug_pmatrix(v, k)
+            Po = oracle.transition_probs(p.model.Eval, p.model.Evec, p.model.Ievc, p.flat.blen[v] * p.rates[k])
+            worst = max(worst, float(np.max(np.abs(P - Po) / Po)))
+    a, b = p.tree.children[0]
+    for k in range(len(p.rates)):
+        Po = oracle.transition_probs(p.model.Eval, p.model.Evec, p.model.Ievc, (p.flat.blen[a] + p.flat.blen[b]) * p.rates[k])
+        worst = max(worst, float(np.max(np.abs(ctx.debug_pmatrix(0, k) - Po) / Po)))
+    assert worst < 1e-12          # same operation order; only CUDA's exp() (<= 1 ulp) can differ
+
+
+@pytest.mark.parametrize("tile_m", [2, 4])
+def test_cfg2_full(ctx, tile_m):
+    p = synthetic(2, 10_000)
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
+    setup(ctx, p, tile_m)
+    check(ctx, p, lnl, joint)
+
+
+def test_cfg3_subset_and_full_size_properties(ctx):
+    p = synthetic(3, 4096)
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
+    setup(ctx, p)
+    check(ctx, p, lnl, joint)
+    # full size: 1,000 taxa x 1M sites = the 4,096 simulated columns repeated; every copy must be bit-identical
+    big = np.tile(p.states, (1, 256))[:, :1_000_000]
+    ctx.set_alignment(big)
+    r = ctx.run(want_joint=False, want_compact=True, threshold=0.5)
+    lnl_big = r["lnl"]
+    assert lnl_big.shape == (1_000_000,)
+    ref = np.tile(lnl_big[:4096], 256)[:1_000_000]
+    assert np.array_equal(lnl_big, ref)
+    assert rel_err(lnl_big[:4096], lnl) < TOL
+    c = r["compact"]
+    assert np.array_equal(c["lnl"], lnl_big)
+    assert rel_err(c["max_prob"][:4096], joint.max(axis=(1, 2))) < TOL
+
+
+def test_cfg4_deep_caterpillar_rescaling(ctx):
+    p = synthetic(4, 1024)
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
+    assert lnl.min() < -3000                                             # log-scale sums far beyond double range
+    setup(ctx, p)
+    check(ctx, p, lnl, joint)
+    ctx.set_option("rescale_every", 3)
+    ctx.set_tree(p.flat)
+    check(ctx, p, lnl, joint)
+    ctx.set_option("rescale_every", 8)
+
+
+def test_cfg5_subset(ctx):
+    p = synthetic(5, 2048)
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
+    setup(ctx, p, 4)
+    check(ctx, p, lnl, joint)
+
+
+def test_ragged_offsets_and_chunks(ctx, example_problem):
+    p = example_problem
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
+    setup(ctx, p)
+    for s0, n in ((0, 1), (129, 1), (37, 5), (1, 129), (16, 17), (0, 0)):
+        r = ctx.run(site0=s0, n=n)
+        assert r["lnl"].shape == (n,)
+        if n:
+            assert rel_err(r["lnl"], lnl[s0:s0 + n]) < TOL and rel_err(r["joint"], joint[s0:s0 + n]) < TOL
+    # chunked pipeline (chunks of 256 columns) and the streamed path give bit-identical results to one launch
+    big = np.tile(p.states, (1, 9))
+    ctx.set_alignment(big)
+    one = ctx.run()
+    ctx.set_option("chunk_cols", 256)
+    many = ctx.run()
+    st = ctx.run_streamed(big)
+    part = ctx.run_streamed(big, site0=131, n=700)
+    ctx.set_option("chunk_cols", 1 << 20)
+    assert np.array_equal(one["lnl"], many["lnl"]) and np.array_equal(one["joint"], many["joint"])
+    assert np.array_equal(one["lnl"], st["lnl"]) and np.array_equal(one["joint"], st["joint"])
+    assert np.array_equal(part["lnl"], one["lnl"][131:831]) and np.array_equal(part["joint"], one["joint"][131:831])
+    assert rel_err(one["lnl"], np.tile(lnl, 9)) < TOL
+
+
+def test_pinned_buffers(ctx, example_problem):
+    p = example_problem
+    setup(ctx, p)
+    n = p.states.shape[1]
+    hl, hj = native.PinnedArray(n, np.float64), native.PinnedArray((n, 20, 20), np.float64)
+    hs = native.PinnedArray(p.states.shape, np.uint8)
+    hs.array[:] = p.states
+    r = ctx.run_streamed(hs.array, out={"lnl": hl.array, "joint": hj.array})
+    ref = ctx.run()
+    assert np.array_equal(r["lnl"], ref["lnl"]) and np.array_equal(hj.array, ref["joint"])
+    for h in (hl, hj, hs):
+        h.free()
+
+
+def test_polytomy_missing_data_custom_rates(ctx):
+    tree = treeio.parse_newick("((a:0.2,b:0.01,f:0.3,(g:0.1,h:0.2):0.0):0.1,(c:0.3,d:0.05,e:0.6):0.02);")   # zero branch -> 1e-9 clamp
+    flat = treeio.flatten_tree(tree)
+    model = oracle.OracleModel("BLOSUM62")
+    states = treeio.encode_alignment(["AV-W", "AV-W", "L--C", "LI-C", "KI-Y", "K?-y", "xV-W", "AB-W"])
+    for rates in (np.array([1.0]), np.array([0.3, 1.7]), np.array([0.0, 0.5, 2.5]), oracle.gamma_rates(8, 0.5)):
+        lnl, joint = oracle.run(flat, states, model, rates)
+        ctx.set_option("tile_m", 2)
+        ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
+        ctx.set_rates(rates)
+        ctx.set_tree(flat)
+        ctx.set_alignment(states)
+        r = ctx.run()
+        assert rel_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
+    assert abs(r["lnl"][2]) < 1e-9                                       # all-missing column: likelihood 1
+
+
+def test_leaf_as_root_child(ctx):
+    """K=1 works in the reference (length-1 shortcut, utils/Utils.java:56-58); K>1 makes the reference throw for
+    that column — the native path returns the well-defined limit instead (documented)."""
+    tree = treeio.parse_newick("(a:0.1,(b:0.2,c:0.3):0.1);")
+    flat = treeio.flatten_tree(tree)
+    model = oracle.OracleModel("WAG")
+    states = treeio.encode_alignment(["A-", "AR", "RR"])
+    lnl1, joint1 = oracle.run(flat, states, model, np.array([1.0]))
+    ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
+    ctx.set_rates(np.array([1.0]))
+    ctx.set_tree(flat)
+    ctx.set_alignment(states)
+    r = ctx.run()
+    assert rel_err(r["lnl"], lnl1) < TOL and rel_err(r["joint"], joint1) < TOL
+    ctx.set_rates(oracle.gamma_rates(4, 0.5))
+    r = ctx.run()
+    assert np.all(np.isfinite(r["lnl"])) and np.max(np.abs(r["joint"].sum(axis=(1, 2)) - 1.0)) < 1e-12
+    assert np.count_nonzero(r["joint"][0].sum(axis=1) > 0) == 1         # state at A is the observed tip state
+
+
+def test_compact_matches_site_result_scan(ctx, example_problem):
+    p = example_problem
+    setup(ctx, p)
+    full = ctx.run()
+    for thr in (0.5, 0.2, 0.0):
+        c = ctx.run(want_joint=False, want_compact=True, threshold=thr)["compact"]
+        for i in range(len(c)):
+            J = full["joint"][i]
+            sr = recon.SiteResult(i, full["lnl"][i], J, thr, sort_by_prob=False)
+            assert c["max_prob"][i] == sr.get_max_prob() and c["max_ii_prob"][i] == sr.get_max_ii_prob()
+            assert c["n_kept"][i] == len(sr.probs)
+            assert bool(c["interesting"][i]) == (sr.get_max_ii_prob() <= 1.0 - thr and sr.get_max_prob() >= thr)
+            k = min(len(sr.probs), 8)
+            assert c["prob"][i][:k].tolist() == sr.probs[:k]
+            if len(sr.probs) <= 8:
+                assert str(recon.SiteResult.from_compact(i, c[i])) == str(recon.SiteResult(i, full["lnl"][i], J, thr))
+
+
+def test_host_mirror_interface(ctx, example_problem):
+    p = example_problem
+    j = recon.JointBranchReconstruction(p.states, p.flat, p.model, p.model.pi, p.rates, sanity_check=True, ctx=ctx)
+    res = j.call()
+    assert len(res) == 130 and res[13].subs[0] == "RK" and str(res[13]).startswith("Result\t14\t-7.0\tRK:1.0")
+
+
+def test_error_behaviour(ctx, example_problem):
+    p = example_problem
+    fresh = native.Context(0)
+    with pytest.raises(native.SrError) as ei:
+        fresh.run(0, 1)
+    assert ei.value.code == -4                                           # SR_ERR_STATE
+    with pytest.raises(native.SrError, match="rate categories"):
+        fresh.set_rates([])
+    bad = treeio.flatten_tree(treeio.parse_newick("(a:1,b:1,c:1);"))
+    with pytest.raises(native.SrError, match="more than two descendents"):
+        fresh.set_tree(bad)
+    setup(fresh, p)
+    with pytest.raises(native.SrError) as ei:
+        fresh.run(100, 31)
+    assert ei.value.code == -1
+    with pytest.raises(native.SrError, match="taxa"):
+        fresh.set_alignment(p.states[:5])
+        fresh.run()
+    with pytest.raises(native.SrError):
+        fresh.set_option("tile_m", 3)
+    fresh.close()
+    with pytest.raises(native.SrError):
+        native.Context(99)
+
+
+def test_profile_and_roofline_hooks(ctx, example_problem):
+    p = example_problem
+    setup(ctx, p)
+    ctx.set_option("profile", 1)
+    ctx.profile(reset=True)
+    ctx.run()
+    prof = ctx.profile(reset=True)
+    ctx.set_option("profile", 0)
+    assert prof["n_prune"] == 1 and prof["n_root"] == 1 and prof["ms_prune"] > 0 and prof["columns_pruned"] == 130
+    info = ctx.schedule_info()
+    assert info["n_steps"] == 34 and info["flops_per_column_rate"] == 55520 / 4      # 55 520 flops/column
+    assert 25.0 < ctx.measure_fp64_peak(50) < 45.0

@@ -1,0 +1,110 @@
+"""Host logic either side of the path: readers, flatteners, SiteResult formatting (no GPU)."""
+import numpy as np
+import pytest
+
+from subrecon_b200 import palmodel, recon, synth, treeio
+
+
+def test_newick_pal_conventions():
+    t = treeio.parse_newick("((a:1,b:2)x:3,(c,d,e)0.95:4);")
+    assert t.children[0] == [1, 4] and t.children[4] == [5, 6, 7]      # Newick order kept, polytomy allowed
+    assert t.blen[1] == 3.0 and t.blen[5] == 0.0                        # missing length = 0.0 (SimpleNode default)
+    assert t.name[2] == "a" and t.name[1] == ""                         # internal labels ignored
+    with pytest.raises(ValueError, match="single child"):
+        treeio.parse_newick("((a:1):2,b:1);")
+    t2 = treeio.parse_newick(" ( a : 1e-3 ,\n b:2.5E-1 ) ; ")
+    assert t2.blen[1] == 1e-3 and t2.blen[2] == 0.25
+
+
+def test_newick_roundtrip_and_depth():
+    t = synth.caterpillar_tree(3000)                                     # deep: must not recurse
+    t2 = treeio.parse_newick(t.to_newick())
+    assert t2.to_newick() == t.to_newick() and t2.n_nodes == t.n_nodes
+
+
+def test_example_inputs(example_problem):
+    p = example_problem
+    assert p.states.shape == (19, 130) and p.states.max() < 20          # 20 letters only, no gaps
+    assert p.flat.n_nodes == 37 and len(p.tree.children[0]) == 2
+    assert len({bytes(p.states[:, c]) for c in range(130)}) == 51      # 51 distinct columns
+    a, b = p.tree.children[0]
+    assert abs(p.tree.blen[a] + p.tree.blen[b] - 0.108120) < 1e-6
+
+
+def test_state_encoding():
+    s = treeio.encode_alignment(["ARNDCQEGHILKMFPSTWYV", "arndcqeghilkmfpstwyv", "-_?.*XBJZOU1 ", "AC"])
+    assert s[0].tolist() == list(range(20)) and s[1].tolist() == list(range(20))
+    assert (s[2, :13] == treeio.MISSING).all()
+    assert s[3, :2].tolist() == [0, 4] and (s[3, 2:] == treeio.MISSING).all()       # padded with '-' to the longest
+
+
+def test_flatten_unknown_taxon():
+    t = treeio.parse_newick("((a:1,b:1):1,(c:1,d:1):1);")
+    with pytest.raises(KeyError):
+        treeio.flatten_tree(t, {"a": 0, "b": 1, "c": 2})
+    f = treeio.flatten_tree(t, {"a": 3, "b": 2, "c": 1, "d": 0})
+    assert f.child_off.tolist() == [0, 2, 4, 4, 4, 6, 6, 6] and f.leaf_row.tolist() == [-1, -1, 3, 2, -1, 1, 0]
+
+
+def test_fasta_and_phylip(tmp_path):
+    fa = tmp_path / "a.fa"
+    fa.write_text(">x one \nAC D\nEF\n>y\nac-\n")
+    names, seqs = treeio.read_fasta(fa)
+    assert names == ["x one", "y"] and seqs == ["ACDEF", "ac-"]
+    ph = tmp_path / "a.phy"
+    ph.write_text(" 2 6\nx  ACD\ny  EFG\n\nHIK\nLMN\n")
+    names, seqs = treeio.read_phylip(ph)
+    assert names == ["x", "y"] and seqs == ["ACDHIK", "EFGLMN"]
+
+
+def test_synthetic_trees():
+    b = synth.balanced_tree(100, 2)
+    assert len(b.leaves()) == 100 and all(len(c) in (0, 2) for c in b.children)
+    y = synth.yule_tree(1000, 3)
+    assert len(y.leaves()) == 1000 and all(len(y.children[c]) == 2 for c in y.children[0])
+    c = synth.caterpillar_tree(5000, 4)
+    assert len(c.leaves()) == 5000 and all(len(c.children[x]) == 2 for x in c.children[0])
+    assert min(c.blen[1:]) >= 1e-3 and max(c.blen) <= 1.0
+
+
+def test_round_and_format():
+    assert recon.round_double(-2.5, 0) == -2.0 and recon.round_double(0.125, 2) == 0.13       # Math.round = floor(x+1/2)
+    assert recon.round_double(-15.664999, 2) == -15.66
+    f = recon.java_double_to_string
+    assert [f(x) for x in (1.0, 0.99, -15.66, 0.0, 1.2e-4, 0.001, 12345678.9, 1e-10)] == \
+        ["1.0", "0.99", "-15.66", "0.0", "1.2E-4", "0.001", "1.23456789E7", "1.0E-10"]
+
+
+def test_site_result_filter_sort_print():
+    p = np.zeros((20, 20))
+    p[1, 11] = 0.3
+    p[0, 0] = 0.25
+    p[2, 3] = 0.3
+    p[5, 5] = 0.15
+    r = recon.SiteResult(13, -7.004, p, threshold=0.2, sort_by_prob=True, sig_digits=2)
+    assert r.get_max_ii_prob() == 0.25 and r.get_max_prob() == 0.3
+    assert r.subs == ["RK", "ND", "AA"]                                  # stable: RK (canonical first) stays before ND
+    assert str(r) == "Result\t14\t-7.0\tRK:0.3\tND:0.3\tAA:0.25"
+    r2 = recon.SiteResult(13, -7.004, p, threshold=0.2, sort_by_prob=False)
+    assert r2.subs == ["AA", "RK", "ND"]
+    assert recon.SiteResult.get_header() == "[HEADER]\tsite\tln[P(D|theta,alpha)]\tP(A=a,B=b|D,theta,alpha)"
+
+
+def test_run_columns_print_rule():
+    p = np.zeros((20, 20)); p[1, 11] = 0.9; p[1, 1] = 0.1
+    q = np.zeros((20, 20)); q[4, 4] = 0.97; q[4, 5] = 0.03
+    rs = [recon.SiteResult(0, -1.0, p), recon.SiteResult(1, -2.0, q)]
+    lines = recon.run_columns(rs)
+    assert lines == ["Result\t1\t-1.0\tRK:0.9", "Total lnL: -3.0000000000"]
+    lines = recon.run_columns([rs[1]])
+    assert lines[0] == "Total lnL: -2.0000000000" and lines[1].startswith("0 sites have non-identical")
+    assert len(recon.run_columns(rs, verbose=True)) == 3
+
+
+def test_cli_frequency_normalisation():
+    f = palmodel.normalise_cli_frequencies(["0.1"] * 20)
+    assert abs(sum(f) - 1.0) < 1e-15
+    with pytest.raises(ValueError):
+        palmodel.normalise_cli_frequencies([0.5, 0.5])
+    with pytest.raises(ValueError, match="not recognised"):
+        palmodel.host_model("lg")
