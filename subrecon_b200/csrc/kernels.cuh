@@ -59,6 +59,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Consumer release of a ring stage that was read with ordinary ld.shared: the reads (generic proxy) must be
+// ordered before the producer's next TMA write (async proxy) to the same bytes. Without this fence the arrive can
+// overtake loads still queued in the LSU and a lagging warp reads a half-overwritten matrix (seen on B200 as
+// run-to-run 1e-12..1e-2 relative noise in the warps sharing an SMSP with the producer).
+__device__ __forceinline__ void stage_release(uint64_t* bar, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -260,8 +269,6 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(PruneParams p) 
                 double Bf[15];
 #pragma unroll
                 for (int i = 0; i < 15; ++i) Bf[i] = sd[i * 32 + lane];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[stage]);
                 double pv[M][5];
                 if (code == OP_MV_MULPOP) {
                     --sp;
@@ -284,6 +291,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(PruneParams p) 
                     for (int j = 0; j < M; ++j)
 #pragma unroll
                         for (int t = 0; t < 3; ++t) dmma(acc[j][t][0], acc[j][t][1], A[j][s], Bf[s * 3 + t]);
+                stage_release(&empty[stage], lane);      // after the MMAs were issued: their operands have left smem
 #pragma unroll
                 for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -304,8 +312,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(PruneParams p) 
                         A[j][r] = (code == OP_LEAF_MUL) ? A[j][r] * v : v;
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[stage]);
+                stage_release(&empty[stage], lane);
             }
             if (w & OPF_RESCALE) {
 #pragma unroll

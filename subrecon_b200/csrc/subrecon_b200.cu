@@ -67,7 +67,8 @@ struct sr_ctx {
 
     // options
     int tile_m = 2;
-    int64_t chunk_cols = 1 << 20;
+    int64_t chunk_cols = 1 << 20;       // resident runs: columns per launch
+    int64_t stream_chunk_cols = 1 << 17; // streamed runs: columns per pipeline stage (H2D | kernels | D2H overlap)
     int rescale_every = 8;
     bool profile = false;
 
@@ -554,7 +555,7 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
     rc = ensure_pstream(c, c->stream);
     if (rc) return rc;
     // three-stage pipeline over column chunks: H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h), two buffers each
-    const int64_t chunk = std::max<int64_t>(256, (std::min<int64_t>(c->chunk_cols, std::max<int64_t>(n, 1)) + 255) / 256 * 256);
+    const int64_t chunk = std::max<int64_t>(256, (std::min<int64_t>(std::min(c->chunk_cols, c->stream_chunk_cols), std::max<int64_t>(n, 1)) + 255) / 256 * 256);
     const int64_t cpitch = chunk + 256;
     cudaEvent_t up_ev[2], done_ev[2], free_ev[2], sfree_ev[2];
     for (int i = 0; i < 2; ++i) {
@@ -620,6 +621,9 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     } else if (k == "chunk_cols") {
         if (value < 256) return fail(c, SR_ERR_ARG, "chunk_cols must be >= 256");
         c->chunk_cols = (value + 255) / 256 * 256;
+    } else if (k == "stream_chunk_cols") {
+        if (value < 256) return fail(c, SR_ERR_ARG, "stream_chunk_cols must be >= 256");
+        c->stream_chunk_cols = (value + 255) / 256 * 256;
     } else if (k == "profile") {
         c->profile = value != 0;
     } else if (k == "rescale_every") {

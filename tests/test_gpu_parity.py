@@ -88,7 +88,9 @@ def test_device_built_matrices_match_pal(ctx, example_problem):
     for k in range(len(p.rates)):
         Po = oracle.transition_probs(p.model.Eval, p.model.Evec, p.model.Ievc, (p.flat.blen[a] + p.flat.blen[b]) * p.rates[k])
         worst = max(worst, float(np.max(np.abs(ctx.debug_pmatrix(0, k) - Po) / Po)))
-    assert worst < 1e-12          # same operation order; only CUDA's exp() (<= 1 ulp) can differ
+    # same operation order as PAL; only CUDA's exp() (<= 1 ulp) can differ. Off-diagonal entries of the 1e-6
+    # branches are ~1e-8 and emerge from cancelling O(1) terms, so 1 ulp there is ~1e-10 relative.
+    assert worst < 1e-9
 
 
 @pytest.mark.parametrize("tile_m", [2, 4])
