@@ -114,6 +114,14 @@ int sr_profile_reset(sr_ctx *ctx);
 /* Schedule facts for the current tree: number of pruning steps, stack depth needed, and the
  * algorithmic flops per column per rate class (820*E_int + 20*E_leaf + 1200). */
 int sr_schedule_info(sr_ctx *ctx, int64_t *n_steps, int32_t *stack_depth, double *flops_per_column_rate);
+/* Host-only (no GPU needed): the fused pruning schedule sr_set_tree would build. steps[4*i..] = {word, alignment
+ * row of tip 0, 1, 2}; word bits: 0-1 MV (1 = A=P·A, 2 = A=pop∘P·A), 2-3 number of tip gathers before the MV,
+ * 4 first gather starts a new partial, 5 one tip gather after the MV, 6 rescale, 7 push, 8/9 store as root child
+ * A/B. node_slot[v] = position of node v's parent edge in the matrix stream (per step: MV first, then tips).
+ * This replaces the recursion order of downTreeMarginal (JointBranchReconstruction.java:191-247). */
+int sr_schedule_dump(int32_t n_nodes, const int32_t *child_off, const int32_t *child_idx, const double *blen,
+                     const int32_t *leaf_row, int32_t root, int32_t rescale_every, int64_t cap_steps, int32_t *steps,
+                     int32_t *node_slot, int64_t *n_steps, int32_t *stack_depth);
 /* Live FP64 roofline probe: runs a register-resident DMMA (mma.sync m8n8k4 f64) loop for ~`ms` and
  * returns TFLOP/s — the denominator bench.py reports the pruning kernel against. */
 int sr_measure_fp64_peak(sr_ctx *ctx, double ms, double *tflops);

@@ -25,27 +25,10 @@
 namespace srk {
 
 constexpr int NS = 20;
-constexpr int SLOT_DOUBLES = 480;                 // one pruning step's matrix in either layout
-constexpr int SLOT_BYTES = SLOT_DOUBLES * 8;      // 3840
-constexpr int LEAF_TABLE_BYTES = 21 * NS * 8;     // 3360: P^T rows for states 0..19 + the missing-data row
-constexpr int STAGE_BYTES = 4096;                 // slot + up to 256 state bytes
-constexpr int N_CONSUMER_WARPS = 8;
-constexpr int PRUNE_THREADS = (N_CONSUMER_WARPS + 1) * 32;
-
-// op word of the pruning schedule
-enum : int32_t {
-    OP_LEAF_SET = 0,        // A  = T[state]
-    OP_LEAF_MUL = 1,        // A *= T[state]
-    OP_MV_SET = 2,          // A  = P·A
-    OP_MV_MULPOP = 3,       // A  = pop() ∘ (P·A)
-    OP_CODE_MASK = 3,
-    OPF_RESCALE = 1 << 2,   // after the op: scale A by a power of two, count the exponent
-    OPF_PUSH = 1 << 3,      // after the op (and rescale): push A
-    OPF_STORE_A = 1 << 4,   // after the op: A is the partial of root child 0
-    OPF_STORE_B = 1 << 5,   // ... of root child 1 (also stores the exponent count)
-    OPF_IDENTITY = 1 << 6,  // K1 only: tip directly below the root, table = identity
-    OP_ROW_SHIFT = 8        // leaf ops: alignment row in bits 8..31
-};
+constexpr int FRAG_DOUBLES = 480;                 // a 20x20 matrix as 15 DMMA B-fragments x 32 lanes (padded to 24 rows)
+constexpr int FRAG_BYTES = FRAG_DOUBLES * 8;      // 3840
+constexpr int TABLE_DOUBLES = 21 * NS;            // P^T rows for states 0..19 + the missing-data row
+constexpr int TABLE_BYTES = TABLE_DOUBLES * 8;    // 3360
 
 // ------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,30 +75,35 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 // ------------------------------------------------------------------------------------------- K1
+// One "slot" = one transition matrix in the layout its consumer wants.
+enum : int32_t { SLOT_FRAG = 0, SLOT_TABLE = 1, SLOT_IDENTITY = 2 };
+
 struct PBuildParams {
-    const double* eval;      // [20]
-    const double* evec;      // [400]  Evec[i][k]
-    const double* ievc;      // [400]  Ievc[k][j]
-    const double* rates;     // [K]
-    const int32_t* ops;      // [n_ops]
-    const double* op_blen;   // [n_ops] branch length of the edge the step applies
-    double* pstream;         // [K][n_ops][480]
-    double* proot;           // [K][400] row-major, merged root branch
-    double root_blen;        // tA + tB (summed before the rate multiply, JointBranchReconstruction.java:99)
-    int n_ops;
+    const double* eval;        // [20]
+    const double* evec;        // [400]  Evec[i][k]
+    const double* ievc;        // [400]  Ievc[k][j]
+    const double* rates;       // [K]
+    const int32_t* slot_kind;  // [n_slots]
+    const int32_t* slot_off;   // [n_slots] offset (doubles) inside one rate class's stream
+    const double* slot_blen;   // [n_slots] branch length of the edge
+    double* pstream;           // [K][rate_stride]
+    double* proot;             // [K][400] row-major, merged root branch
+    int64_t rate_stride;       // doubles per rate class
+    double root_blen;          // tA + tB (summed before the rate multiply, JointBranchReconstruction.java:99)
+    int n_slots;
     int K;
 };
 
-// grid (n_ops + 1, K); block 128. Block x == n_ops builds the root-branch matrix.
+// grid (n_slots + 1, K); block 128. Block x == n_slots builds the root-branch matrix.
 __global__ void __launch_bounds__(128) pbuild_kernel(PBuildParams p) {
     __shared__ double iexp[NS * NS];
     __shared__ double P[NS * NS];
-    const int op = blockIdx.x, k = blockIdx.y, tid = threadIdx.x;
-    const bool is_root = (op == p.n_ops);
-    const int32_t w = is_root ? 0 : p.ops[op];
+    const int slot = blockIdx.x, k = blockIdx.y, tid = threadIdx.x;
+    const bool is_root = (slot == p.n_slots);
+    const int kind = is_root ? -1 : p.slot_kind[slot];
     const double rate = p.rates[k];
     // same expression order as the reference: child.getBranchLength() * rate  /  (tA + tB) * rate
-    double t = (is_root ? p.root_blen : p.op_blen[op]) * rate;
+    double t = (is_root ? p.root_blen : p.slot_blen[slot]) * rate;
     if (t < 1e-9) t = 1e-9;                                        // MatrixExponential::setDistance @0-11
     for (int e = tid; e < NS * NS; e += 128) {
         const int kk = e / NS;
@@ -134,11 +122,10 @@ __global__ void __launch_bounds__(128) pbuild_kernel(PBuildParams p) {
         for (int e = tid; e < NS * NS; e += 128) p.proot[(size_t)k * NS * NS + e] = P[e];
         return;
     }
-    double* out = p.pstream + ((size_t)k * p.n_ops + op) * SLOT_DOUBLES;
-    const int code = w & OP_CODE_MASK;
-    if (code >= OP_MV_SET) {
-        // B-fragments: slot (s*3+t)*32 + lane = P[5(g/2) + 2t + (g&1)][5q + s], g = lane>>2, q = lane&3
-        for (int e = tid; e < SLOT_DOUBLES; e += 128) {
+    double* out = p.pstream + (size_t)k * p.rate_stride + p.slot_off[slot];
+    if (kind == SLOT_FRAG) {
+        // B-fragments: (s*3+t)*32 + lane = P[5(g/2) + 2t + (g&1)][5q + s], g = lane>>2, q = lane&3
+        for (int e = tid; e < FRAG_DOUBLES; e += 128) {
             const int lane = e & 31, st = e >> 5, s = st / 3, tt = st % 3;
             const int g = lane >> 2, q = lane & 3;
             const int r = 2 * tt + (g & 1);
@@ -147,57 +134,93 @@ __global__ void __launch_bounds__(128) pbuild_kernel(PBuildParams p) {
     } else {
         // gather table T[s][i] = P[i][s]; row 20 = Σ_j P[i][j] (a missing tip is the all-ones vector,
         // JointBranchReconstruction.java:201-205, so its contribution is the row sum, left to right)
-        const bool ident = (w & OPF_IDENTITY) != 0;
-        for (int e = tid; e < SLOT_DOUBLES; e += 128) {
-            double v = 0.0;
-            if (e < 21 * NS) {
-                const int s = e / NS, i = e % NS;
-                if (s < NS) v = ident ? (i == s ? 1.0 : 0.0) : P[i * NS + s];
-                else if (ident) v = 1.0;
-                else {
-                    double acc = 0.0;
-                    for (int j = 0; j < NS; ++j) acc = __dadd_rn(acc, P[i * NS + j]);
-                    v = acc;
-                }
+        const bool ident = (kind == SLOT_IDENTITY);
+        for (int e = tid; e < TABLE_DOUBLES; e += 128) {
+            const int s = e / NS, i = e % NS;
+            double v;
+            if (s < NS) v = ident ? (i == s ? 1.0 : 0.0) : P[i * NS + s];
+            else if (ident) v = 1.0;
+            else {
+                double acc = 0.0;
+                for (int j = 0; j < NS; ++j) acc = __dadd_rn(acc, P[i * NS + j]);
+                v = acc;
             }
             out[e] = v;
         }
     }
 }
 
+// ------------------------------------------------------------------------------------------- K0
+// In-place clamp of the uploaded state codes to 0..20 (20 = missing data: any code outside 0..19,
+// JointBranchReconstruction.java:199-205), so the pruning kernel can index its 21-row gather tables directly.
+__global__ void __launch_bounds__(256) sanitize_kernel(uint4* __restrict__ v, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 x = v[i];
+        x.x = __vminu4(x.x, 0x14141414u); x.y = __vminu4(x.y, 0x14141414u);
+        x.z = __vminu4(x.z, 0x14141414u); x.w = __vminu4(x.w, 0x14141414u);
+        v[i] = x;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- K2
+// A pruning STEP (one ring stage, one loop iteration of a consumer warp) applies up to four edges:
+//     A  = / *=  T_pre0[state]          (n_pre >= 1; "=" when the step starts a new partial)
+//     A *= T_pre1[state]                (n_pre == 2)
+//     A  = P·A  [∘ pop()]               (mv: 1 = set, 2 = multiply with the popped sibling partial)
+//     A *= T_post[state]                (n_post == 1, only together with an MV)
+// then optionally rescales, pushes A, or stores it as a root-child partial. In a binary tree nearly every step
+// carries one MV (30·M DMMAs per warp), so the per-iteration bookkeeping and the tip gathers overlap an MMA burst.
+enum : int32_t {
+    ST_MV_MASK = 3,          // bits 0-1
+    ST_NPRE_SHIFT = 2,       // bits 2-3
+    ST_PRE0_SET = 1 << 4,
+    ST_NPOST = 1 << 5,
+    STF_RESCALE = 1 << 6,
+    STF_PUSH = 1 << 7,
+    STF_STORE_A = 1 << 8,
+    STF_STORE_B = 1 << 9,
+    STF_ANY = STF_RESCALE | STF_PUSH | STF_STORE_A | STF_STORE_B
+};
+
 struct PruneParams {
-    const int32_t* ops;        // [n_ops]
-    const double* pstream;     // [K][n_ops][480]
+    const int4* steps;         // [n_steps] {word, row of leaf 0, 1, 2}
+    const int32_t* step_off;   // [n_steps] offset (doubles) of the step's matrices inside one rate class's stream
+    const double* pstream;     // [K][rate_stride]
     const uint8_t* states;     // device alignment block, states[row*pitch + col]
+    int64_t rate_stride;
     int64_t pitch;
     int64_t col0;              // first column of this launch inside the block (multiple of 16)
     double* rootpart;          // [2][K][ncp][20]
     int32_t* rootexp;          // [K][ncp]
     double* spill;             // global overflow of the partial stack
     int64_t ncp;               // padded column count of this launch (n_tiles * S)
-    int n_ops;
+    int n_steps;
     int n_tiles;
     int K;
     int smem_levels;           // stack levels resident in shared memory
     int spill_levels;
 };
 
-template <int M>
+template <int M, int W_>
 struct PruneCfg {
-    static constexpr int W = N_CONSUMER_WARPS;
+    static constexpr int W = W_;                        // consumer warps (+1 producer warp)
+    static constexpr int THREADS = (W_ + 1) * 32;
     static constexpr int S = W * M * 8;                 // columns per work item
     static constexpr int LEVEL_DOUBLES = W * M * 5 * 32;
     static constexpr int LEVEL_BYTES = LEVEL_DOUBLES * 8;
+    static constexpr int STATES_OFF = FRAG_BYTES + 3 * TABLE_BYTES;                 // 13920
+    static constexpr int STAGE_BYTES = ((STATES_OFF + 3 * S + 127) / 128) * 128;
 };
 
 __host__ __device__ constexpr int prune_bar_bytes(int nstage) { return ((2 * nstage * 8 + 127) / 128) * 128; }
 
-template <int M, int NSTAGE>
-__global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(PruneParams p) {
-    using Cfg = PruneCfg<M>;
+template <int M, int NSTAGE, int W_>
+__global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) {
+    using Cfg = PruneCfg<M, W_>;
     constexpr int W = Cfg::W;
     constexpr int S = Cfg::S;
+    constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int TILE_DOUBLES = M * 5 * 32;            // one warp's partial on the stack
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stages = smem;                                             // NSTAGE * STAGE_BYTES
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
@@ -215,35 +238,36 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(PruneParams p) 
     uint32_t it = 0;                                  // ring position, runs on across work items
 
     if (warp == W) {
-        // ===== producer: one lane streams every step's matrix (and tip states) into the ring =====
+        // ===== producer: one lane streams every step's matrices (and tip states) into the ring =====
         if (lane == 0) {
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int k = item / p.n_tiles, tile = item - k * p.n_tiles;
-                const double* ps = p.pstream + (size_t)k * p.n_ops * SLOT_DOUBLES;
+                const double* ps = p.pstream + (size_t)k * p.rate_stride;
                 const uint8_t* st = p.states + p.col0 + (int64_t)tile * S;
-                for (int op = 0; op < p.n_ops; ++op, ++it) {
+                for (int step = 0; step < p.n_steps; ++step, ++it) {
                     const int stage = it % NSTAGE;
                     const uint32_t ph = (it / NSTAGE) & 1;
-                    const int32_t w = p.ops[op];
+                    const int4 d = __ldg(p.steps + step);
+                    const int n_leaf = ((d.x >> ST_NPRE_SHIFT) & 3) + ((d.x & ST_NPOST) ? 1 : 0);
+                    const uint32_t pbytes = ((d.x & ST_MV_MASK) ? FRAG_BYTES : 0) + n_leaf * TABLE_BYTES;
                     mbar_wait(&empty[stage], ph ^ 1);
                     unsigned char* dst = stages + stage * STAGE_BYTES;
-                    if ((w & OP_CODE_MASK) >= OP_MV_SET) {
-                        mbar_expect_tx(&full[stage], SLOT_BYTES);
-                        bulk_g2s(dst, ps + (size_t)op * SLOT_DOUBLES, SLOT_BYTES, &full[stage]);
-                    } else {
-                        mbar_expect_tx(&full[stage], LEAF_TABLE_BYTES + S);
-                        bulk_g2s(dst, ps + (size_t)op * SLOT_DOUBLES, LEAF_TABLE_BYTES, &full[stage]);
-                        bulk_g2s(dst + SLOT_BYTES, st + (int64_t)(uint32_t(w) >> OP_ROW_SHIFT) * p.pitch, S, &full[stage]);
-                    }
+                    mbar_expect_tx(&full[stage], pbytes + n_leaf * S);
+                    bulk_g2s(dst, ps + __ldg(p.step_off + step), pbytes, &full[stage]);
+                    if (n_leaf > 0) bulk_g2s(dst + Cfg::STATES_OFF, st + (int64_t)d.y * p.pitch, S, &full[stage]);
+                    if (n_leaf > 1) bulk_g2s(dst + Cfg::STATES_OFF + S, st + (int64_t)d.z * p.pitch, S, &full[stage]);
+                    if (n_leaf > 2) bulk_g2s(dst + Cfg::STATES_OFF + 2 * S, st + (int64_t)d.w * p.pitch, S, &full[stage]);
                 }
             }
         }
         return;
     }
 
-    // ===== consumers: 8 warps, each walks the whole schedule for its own 8*M columns =====
+    // ===== consumers: W warps, each walks the whole schedule for its own 8*M columns =====
     const int g = lane >> 2, q = lane & 3;
-    double* spill_base = p.spill + ((size_t)blockIdx.x * W + warp) * (size_t)p.spill_levels * (M * 5 * 32);
+    double* spill_base = p.spill + ((size_t)blockIdx.x * W + warp) * (size_t)p.spill_levels * TILE_DOUBLES;
+    double* my_stack = stack + warp * TILE_DOUBLES + lane;
+    const int st_lane_off = Cfg::STATES_OFF + warp * (M * 8) + g;
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int k = item / p.n_tiles, tile = item - k * p.n_tiles;
@@ -256,29 +280,73 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(PruneParams p) 
             for (int r = 0; r < 5; ++r) A[j][r] = 0.0;
         }
         int sp = 0;
-        int32_t w_next = p.ops[0];
-        for (int op = 0; op < p.n_ops; ++op, ++it) {
+        int w_next = __ldg(&p.steps[0].x);
+        for (int step = 0; step < p.n_steps; ++step, ++it) {
             const int stage = it % NSTAGE;
             const uint32_t ph = (it / NSTAGE) & 1;
-            const int32_t w = w_next;
-            if (op + 1 < p.n_ops) w_next = p.ops[op + 1];
+            const int w = w_next;
+            if (step + 1 < p.n_steps) w_next = __ldg(&p.steps[step + 1].x);
+            const int mv = w & ST_MV_MASK, n_pre = (w >> ST_NPRE_SHIFT) & 3;
+            const unsigned char* stg = stages + stage * STAGE_BYTES;
+            const double* frag = reinterpret_cast<const double*>(stg) + lane;
+            const double* tab = reinterpret_cast<const double*>(stg + (mv ? FRAG_BYTES : 0)) + q * 5;
+            const unsigned char* stb = stg + st_lane_off;
             mbar_wait(&full[stage], ph);
-            const double* sd = reinterpret_cast<const double*>(stages + stage * STAGE_BYTES);
-            const int code = w & OP_CODE_MASK;
-            if (code >= OP_MV_SET) {
-                double Bf[15];
+
+            // ---- all shared-memory reads of the step are issued up front
+            int s0[M], s1[M], s2[M];
 #pragma unroll
-                for (int i = 0; i < 15; ++i) Bf[i] = sd[i * 32 + lane];
-                double pv[M][5];
-                if (code == OP_MV_MULPOP) {
-                    --sp;
-                    const double* src = (sp < p.smem_levels)
-                        ? stack + ((size_t)sp * W + warp) * (M * 5 * 32)
-                        : spill_base + (size_t)(sp - p.smem_levels) * (M * 5 * 32);
+            for (int j = 0; j < M; ++j) { s0[j] = stb[j * 8]; s1[j] = stb[S + j * 8]; s2[j] = stb[2 * S + j * 8]; }
+            double Bf[15];
+            if (mv) {
+#pragma unroll
+                for (int i = 0; i < 15; ++i) Bf[i] = frag[i * 32];
+            }
+            constexpr bool LAZY = (M >= 4);      // big tiles: fetch the post-MMA operands after the burst (registers)
+            double pv[M][5];
+            if (mv == 2) --sp;
+            if (mv == 2 && !LAZY) {
+                if (sp < p.smem_levels) {                                  // warp-uniform: LDS, not a generic load
+                    const double* src = my_stack + (size_t)sp * (W * TILE_DOUBLES);
 #pragma unroll
                     for (int j = 0; j < M; ++j)
 #pragma unroll
-                        for (int r = 0; r < 5; ++r) pv[j][r] = src[(j * 5 + r) * 32 + lane];
+                        for (int r = 0; r < 5; ++r) pv[j][r] = src[(j * 5 + r) * 32];
+                } else {
+                    const double* src = spill_base + (size_t)(sp - p.smem_levels) * TILE_DOUBLES + lane;
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) pv[j][r] = __ldcg(src + (j * 5 + r) * 32);
+                }
+            }
+            // ---- tips below this node (gathers of P^T rows by observed state)
+            if (n_pre >= 1) {
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    const double* row = tab + s0[j] * NS;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) A[j][r] = (w & ST_PRE0_SET) ? row[r] : A[j][r] * row[r];
+                }
+            }
+            if (n_pre == 2) {
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    const double* row = tab + TABLE_DOUBLES + s1[j] * NS;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) A[j][r] *= row[r];
+                }
+            }
+            if (mv) {
+                double vp[M][5];
+                if ((w & ST_NPOST) && !LAZY) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) {
+                        const int sx = n_pre == 0 ? s0[j] : (n_pre == 1 ? s1[j] : s2[j]);
+                        const double* row = tab + n_pre * TABLE_DOUBLES + sx * NS;
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) vp[j][r] = row[r];
+                    }
                 }
                 double acc[M][3][2];
 #pragma unroll
@@ -291,61 +359,109 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(PruneParams p) 
                     for (int j = 0; j < M; ++j)
 #pragma unroll
                         for (int t = 0; t < 3; ++t) dmma(acc[j][t][0], acc[j][t][1], A[j][s], Bf[s * 3 + t]);
-                stage_release(&empty[stage], lane);      // after the MMAs were issued: their operands have left smem
+                if (LAZY) {
+                    if (w & ST_NPOST) {
+#pragma unroll
+                        for (int j = 0; j < M; ++j) {
+                            const int sx = n_pre == 0 ? s0[j] : (n_pre == 1 ? s1[j] : s2[j]);
+                            const double* row = tab + n_pre * TABLE_DOUBLES + sx * NS;
+#pragma unroll
+                            for (int r = 0; r < 5; ++r) vp[j][r] = row[r];
+                        }
+                    }
+                    if (mv == 2) {
+                        if (sp < p.smem_levels) {
+                            const double* src = my_stack + (size_t)sp * (W * TILE_DOUBLES);
+#pragma unroll
+                            for (int j = 0; j < M; ++j)
+#pragma unroll
+                                for (int r = 0; r < 5; ++r) pv[j][r] = src[(j * 5 + r) * 32];
+                        } else {
+                            const double* src = spill_base + (size_t)(sp - p.smem_levels) * TILE_DOUBLES + lane;
+#pragma unroll
+                            for (int j = 0; j < M; ++j)
+#pragma unroll
+                                for (int r = 0; r < 5; ++r) pv[j][r] = __ldcg(src + (j * 5 + r) * 32);
+                        }
+                    }
+                }
+                if (!LAZY) stage_release(&empty[stage], lane);   // every operand of the step left shared memory before the burst
 #pragma unroll
                 for (int j = 0; j < M; ++j)
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) {
-                        const double o = acc[j][r >> 1][r & 1];
-                        A[j][r] = (code == OP_MV_MULPOP) ? o * pv[j][r] : o;
-                    }
-            } else {
-                const unsigned char* st = stages + stage * STAGE_BYTES + SLOT_BYTES + warp * (M * 8) + g;
+                    for (int r = 0; r < 5; ++r) A[j][r] = acc[j][r >> 1][r & 1];
+                if (mv == 2) {
 #pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    int s = st[j * 8];
-                    s = s > NS ? NS : s;
-                    const double* row = sd + s * NS + q * 5;
+                    for (int j = 0; j < M; ++j)
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) {
-                        const double v = row[r];
-                        A[j][r] = (code == OP_LEAF_MUL) ? A[j][r] * v : v;
-                    }
+                        for (int r = 0; r < 5; ++r) A[j][r] *= pv[j][r];
                 }
+                if (w & ST_NPOST) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) A[j][r] *= vp[j][r];
+                }
+                if (LAZY) {
+                    // the late gathers are consumed by the multiplies above; pin those before the release so that the
+                    // (in-order) arrive cannot be issued while a load from this stage is still in flight
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) asm volatile("" : "+d"(A[j][r]));
+                    stage_release(&empty[stage], lane);
+                }
+            } else {
                 stage_release(&empty[stage], lane);
             }
-            if (w & OPF_RESCALE) {
+            if (w & STF_ANY) {
+                if (w & STF_RESCALE) {
+                    // Power-of-two rescale done entirely in the integer pipe (the FP64 pipe is the one the MMAs need):
+                    // conditionals are >= 0, so the largest one has the largest high word; scaling by 2^-(e-1023)
+                    // is a subtraction in the exponent field. Entries more than 2^-1000 below the maximum flush to 0.
 #pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    double mx = fmax(fmax(fmax(A[j][0], A[j][1]), fmax(A[j][2], A[j][3])), A[j][4]);
-                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-                    const int e = (__double2hiint(mx) >> 20) & 0x7ff;
-                    const double sc = __hiloint2double((2046 - e) << 20, 0);      // 2^(1023-e), exact
+                    for (int j = 0; j < M; ++j) {
+                        int hmx = max(max(max(__double2hiint(A[j][0]), __double2hiint(A[j][1])),
+                                          max(__double2hiint(A[j][2]), __double2hiint(A[j][3]))), __double2hiint(A[j][4]));
+                        hmx = max(hmx, __shfl_xor_sync(0xffffffffu, hmx, 1));
+                        hmx = max(hmx, __shfl_xor_sync(0xffffffffu, hmx, 2));
+                        const int e = (hmx >> 20) & 0x7ff;
+                        const int delta = (e - 1023) << 20;
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) A[j][r] *= sc;
-                    cnt[j] += e - 1023;
+                        for (int r = 0; r < 5; ++r) {
+                            const int hi = __double2hiint(A[j][r]);
+                            const int nh = hi - delta;
+                            A[j][r] = (e != 0 && nh >= 0x00100000) ? __hiloint2double(nh, __double2loint(A[j][r])) : (e != 0 ? 0.0 : A[j][r]);
+                        }
+                        if (e != 0) cnt[j] += e - 1023;
+                    }
                 }
-            }
-            if (w & OPF_PUSH) {
-                double* dst = (sp < p.smem_levels)
-                    ? stack + ((size_t)sp * W + warp) * (M * 5 * 32)
-                    : spill_base + (size_t)(sp - p.smem_levels) * (M * 5 * 32);
+                if (w & STF_PUSH) {
+                    if (sp < p.smem_levels) {
+                        double* dst = my_stack + (size_t)sp * (W * TILE_DOUBLES);
 #pragma unroll
-                for (int j = 0; j < M; ++j)
+                        for (int j = 0; j < M; ++j)
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) dst[(j * 5 + r) * 32 + lane] = A[j][r];
-                ++sp;
-            }
-            if (w & (OPF_STORE_A | OPF_STORE_B)) {
-                const int which = (w & OPF_STORE_B) ? 1 : 0;
+                            for (int r = 0; r < 5; ++r) dst[(j * 5 + r) * 32] = A[j][r];
+                    } else {
+                        double* dst = spill_base + (size_t)(sp - p.smem_levels) * TILE_DOUBLES + lane;
 #pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    const int64_t col = (int64_t)tile * S + warp * (M * 8) + j * 8 + g;
-                    double* dst = p.rootpart + (((size_t)which * p.K + k) * p.ncp + col) * NS + q * 5;
+                        for (int j = 0; j < M; ++j)
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) dst[r] = A[j][r];
-                    if (which == 1 && q == 0) p.rootexp[(size_t)k * p.ncp + col] = cnt[j];
+                            for (int r = 0; r < 5; ++r) __stcg(dst + (j * 5 + r) * 32, A[j][r]);
+                    }
+                    ++sp;
+                }
+                if (w & (STF_STORE_A | STF_STORE_B)) {
+                    const int which = (w & STF_STORE_B) ? 1 : 0;
+#pragma unroll
+                    for (int j = 0; j < M; ++j) {
+                        const int64_t col = (int64_t)tile * S + warp * (M * 8) + j * 8 + g;
+                        double* dst = p.rootpart + (((size_t)which * p.K + k) * p.ncp + col) * NS + q * 5;
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) dst[r] = A[j][r];
+                        if (which == 1 && q == 0) p.rootexp[(size_t)k * p.ncp + col] = cnt[j];
+                    }
                 }
             }
         }

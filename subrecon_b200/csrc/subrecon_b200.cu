@@ -56,9 +56,12 @@ struct sr_ctx {
     int32_t n_nodes = 0, root = 0;
     std::vector<int32_t> child_off, child_idx, leaf_row;
     std::vector<double> blen;
-    std::vector<int32_t> ops;           // schedule
-    std::vector<double> op_blen;
-    std::vector<int32_t> node_op;       // node -> op index that applies its parent edge (-1: none)
+    std::vector<int32_t> steps;         // fused schedule: 4 ints per step {word, leaf row 0, 1, 2}
+    std::vector<int32_t> step_off;      // per step: offset (doubles) of its matrices in a rate class's stream
+    std::vector<int32_t> slot_kind, slot_off;   // per edge: layout kind + offset (doubles)
+    std::vector<double> slot_blen;
+    std::vector<int32_t> node_slot;     // node -> slot that applies its parent edge (-1: none)
+    int64_t rate_stride = 0;            // doubles per rate class
     int need_depth = 0;
     int64_t e_int = 0, e_leaf = 0;
     int32_t max_leaf_row = -1;
@@ -67,13 +70,14 @@ struct sr_ctx {
 
     // options
     int tile_m = 2;
+    int warps = 11;                     // consumer warps per CTA (tile_m == 2 only: 8, 11 or 15)
     int64_t chunk_cols = 1 << 20;       // resident runs: columns per launch
     int64_t stream_chunk_cols = 1 << 17; // streamed runs: columns per pipeline stage (H2D | kernels | D2H overlap)
     int rescale_every = 8;
     bool profile = false;
 
     // device state
-    DevBuf d_model, d_rates, d_ops, d_opblen, d_pstream, d_proot, d_states, d_rootpart, d_rootexp, d_spill;
+    DevBuf d_model, d_rates, d_steps, d_stepoff, d_slotkind, d_slotoff, d_slotblen, d_pstream, d_proot, d_states, d_rootpart, d_rootexp, d_spill;
     DevBuf d_chunk_states[2], d_chunk_lnl[2], d_chunk_joint[2], d_chunk_compact[2], d_peak;
     int32_t aln_taxa = 0;
     int64_t aln_sites = 0, aln_pitch = 0;
@@ -151,37 +155,16 @@ int build_schedule(sr_ctx* c) {
         for (int x : tips) ord[e++] = x;
     }
 
-    c->ops.clear();
-    c->op_blen.clear();
-    c->node_op.assign(n, -1);
-    c->e_int = c->e_leaf = 0;
-    c->max_leaf_row = -1;
-    const int T = std::max(1, c->rescale_every);
-    int s_cur = 0;                               // edges multiplied into A since its last rescale
-    std::vector<int> s_stack;
-
-    auto emit = [&](int code, int child, bool identity) {
-        int32_t w = code;
-        if (code <= OP_LEAF_MUL) {
-            w |= (int32_t)((uint32_t)c->leaf_row[child] << OP_ROW_SHIFT);
-            c->max_leaf_row = std::max(c->max_leaf_row, c->leaf_row[child]);
-        }
-        if (identity) w |= OPF_IDENTITY;
-        c->ops.push_back(w);
-        c->op_blen.push_back(c->blen[child]);
-        c->node_op[child] = (int)c->ops.size() - 1;
-        if (!identity) { if (code <= OP_LEAF_MUL) ++c->e_leaf; else ++c->e_int; }
-        if (code == OP_LEAF_SET) s_cur = 1;
-        else if (code == OP_MV_MULPOP) { s_cur += 1 + s_stack.back(); s_stack.pop_back(); }
-        else s_cur += 1;
-        if (s_cur >= T) { c->ops.back() |= OPF_RESCALE; s_cur = 0; }
-    };
-
+    // ---- primitive edge operations in execution order
+    enum { P_LEAF_SET, P_LEAF_MUL, P_MV_SET, P_MV_MULPOP };
+    struct Prim { int code; int child; bool identity, push, store_a, store_b; };
+    std::vector<Prim> prims;
+    prims.reserve(n);
     struct Frame { int v; int i; };              // i = next position in ord[] of v
     for (int which = 0; which < 2; ++which) {
         const int r = which == 0 ? rc0 : rc1;
         if (is_leaf(r)) {
-            emit(OP_LEAF_SET, r, /*identity=*/true);
+            prims.push_back({P_LEAF_SET, r, true, false, false, false});
         } else {
             std::vector<Frame> fr{{r, 0}};
             while (!fr.empty()) {
@@ -190,25 +173,99 @@ int build_schedule(sr_ctx* c) {
                 if (f.i == deg) {                          // node complete: hand the partial to the parent
                     fr.pop_back();
                     if (!fr.empty()) {
-                        Frame& pf = fr.back();
-                        const bool first = (pf.i == 1);    // v was ord[0] of its parent
-                        emit(first ? OP_MV_SET : OP_MV_MULPOP, v, false);
+                        const bool first = (fr.back().i == 1);    // v was ord[0] of its parent
+                        prims.push_back({first ? P_MV_SET : P_MV_MULPOP, v, false, false, false, false});
                     }
                     continue;
                 }
                 const int ch = ord[off[v] + f.i];
                 if (!is_leaf(ch)) {
-                    if (f.i > 0) { c->ops.back() |= OPF_PUSH; s_stack.push_back(s_cur); }
+                    if (f.i > 0) prims.back().push = true;        // keep the partial while the sibling subtree runs
                     ++f.i;
                     fr.push_back({ch, 0});
                 } else {
-                    emit(f.i == 0 ? OP_LEAF_SET : OP_LEAF_MUL, ch, false);
+                    prims.push_back({f.i == 0 ? P_LEAF_SET : P_LEAF_MUL, ch, false, false, false, false});
                     ++f.i;
                 }
             }
         }
-        c->ops.back() |= (which == 0 ? OPF_STORE_A : OPF_STORE_B);
+        (which == 0 ? prims.back().store_a : prims.back().store_b) = true;
     }
+
+    // ---- fuse into steps: [<=2 tip gathers] [one MV] [<=1 tip gather]; a push/store ends its step
+    c->steps.clear(); c->step_off.clear();
+    c->slot_kind.clear(); c->slot_off.clear(); c->slot_blen.clear();
+    c->node_slot.assign(n, -1);
+    c->e_int = c->e_leaf = 0;
+    c->max_leaf_row = -1;
+    const int T = std::max(1, c->rescale_every);
+    int s_cur = 0;                               // edges multiplied into A since its last rescale
+    std::vector<int> s_stack;
+    int64_t off_d = 0;
+    auto add_slot = [&](const Prim& pr) {
+        const bool leaf = pr.code <= P_LEAF_MUL;
+        c->slot_kind.push_back(pr.identity ? SLOT_IDENTITY : (leaf ? SLOT_TABLE : SLOT_FRAG));
+        c->slot_off.push_back((int32_t)off_d);
+        c->slot_blen.push_back(c->blen[pr.child]);
+        c->node_slot[pr.child] = (int)c->slot_kind.size() - 1;
+        off_d += leaf ? TABLE_DOUBLES : FRAG_DOUBLES;
+        if (!pr.identity) { if (leaf) ++c->e_leaf; else ++c->e_int; }
+        if (leaf) c->max_leaf_row = std::max(c->max_leaf_row, c->leaf_row[pr.child]);
+    };
+    size_t i = 0;
+    while (i < prims.size()) {
+        int32_t word = 0, rows[3] = {0, 0, 0};
+        int n_leaf = 0, n_pre = 0;
+        bool ended = false;                      // a push/store flag closes the step
+        const size_t first = i;
+        // the step's matrices are laid out [MV fragments][tables...] — find the MV (if any) first
+        size_t j = i;
+        int pre = 0;
+        while (j < prims.size() && prims[j].code <= P_LEAF_MUL && pre < 2 && !(j > i && prims[j].code == P_LEAF_SET)) {
+            ++pre; ++j;
+            if (prims[j - 1].push || prims[j - 1].store_a || prims[j - 1].store_b) { ended = true; break; }
+        }
+        size_t mv_at = (size_t)-1;
+        if (!ended && j < prims.size() && prims[j].code >= P_MV_SET) mv_at = j;
+        c->step_off.push_back((int32_t)off_d);
+        if (mv_at != (size_t)-1) add_slot(prims[mv_at]);
+        for (size_t t = i; t < i + pre; ++t) {
+            const Prim& pr = prims[t];
+            if (t == first && pr.code == P_LEAF_SET) { word |= ST_PRE0_SET; s_cur = 0; }
+            add_slot(pr);
+            rows[n_leaf++] = c->leaf_row[pr.child];
+            ++n_pre; ++s_cur;
+        }
+        i += pre;
+        const Prim* last = &prims[i - (pre ? 1 : 0)];
+        if (mv_at != (size_t)-1) {
+            const Prim& pr = prims[mv_at];
+            word |= (pr.code == P_MV_SET) ? 1 : 2;
+            if (pr.code == P_MV_MULPOP) { s_cur += s_stack.back(); s_stack.pop_back(); }
+            ++s_cur;
+            last = &pr;
+            i = mv_at + 1;
+            ended = pr.push || pr.store_a || pr.store_b;
+            if (!ended && i < prims.size() && prims[i].code == P_LEAF_MUL) {
+                const Prim& pl = prims[i];
+                add_slot(pl);
+                rows[n_leaf++] = c->leaf_row[pl.child];
+                word |= ST_NPOST;
+                ++s_cur;
+                last = &pl;
+                ++i;
+            }
+        }
+        word |= n_pre << ST_NPRE_SHIFT;
+        if (s_cur >= T) { word |= STF_RESCALE; s_cur = 0; }
+        if (last->push) { word |= STF_PUSH; s_stack.push_back(s_cur); }
+        if (last->store_a) word |= STF_STORE_A;
+        if (last->store_b) word |= STF_STORE_B;
+        c->steps.push_back(word);
+        c->steps.push_back(rows[0]); c->steps.push_back(rows[1]); c->steps.push_back(rows[2]);
+        if (off_d > INT32_MAX - 4096) return fail(c, SR_ERR_UNSUPPORTED, "tree too large for 32-bit matrix-stream offsets");
+    }
+    c->rate_stride = off_d;
     c->need_depth = std::max(is_leaf(rc0) ? 0 : need[rc0], is_leaf(rc1) ? 0 : need[rc1]);
     c->root_blen = c->blen[rc0] + c->blen[rc1];
     c->sched_dirty = false;
@@ -235,45 +292,55 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
         return fail(c, SR_ERR_STATE, "model, rates and tree must be set before running");
     if (c->sched_dirty) { int rc = build_schedule(c); if (rc) return rc; }
     if (!c->p_dirty) return SR_OK;
-    const int n_ops = (int)c->ops.size();
+    const int n_steps = (int)c->steps.size() / 4, n_slots = (int)c->slot_kind.size();
     CUDA_TRY(c, c->d_model.reserve(sizeof(double) * 840));
     CUDA_TRY(c, c->d_rates.reserve(sizeof(double) * c->K));
-    CUDA_TRY(c, c->d_ops.reserve(sizeof(int32_t) * n_ops));
-    CUDA_TRY(c, c->d_opblen.reserve(sizeof(double) * n_ops));
-    CUDA_TRY(c, c->d_pstream.reserve(sizeof(double) * (size_t)c->K * n_ops * SLOT_DOUBLES));
+    CUDA_TRY(c, c->d_steps.reserve(sizeof(int32_t) * 4 * n_steps));
+    CUDA_TRY(c, c->d_stepoff.reserve(sizeof(int32_t) * n_steps));
+    CUDA_TRY(c, c->d_slotkind.reserve(sizeof(int32_t) * n_slots));
+    CUDA_TRY(c, c->d_slotoff.reserve(sizeof(int32_t) * n_slots));
+    CUDA_TRY(c, c->d_slotblen.reserve(sizeof(double) * n_slots));
+    CUDA_TRY(c, c->d_pstream.reserve(sizeof(double) * (size_t)c->K * c->rate_stride));
     CUDA_TRY(c, c->d_proot.reserve(sizeof(double) * (size_t)c->K * 400));
     double hm[840];
     memcpy(hm, c->eval, 160); memcpy(hm + 20, c->evec, 3200); memcpy(hm + 420, c->ievc, 3200); memcpy(hm + 820, c->pi, 160);
-    // plain synchronous copies: these are tiny, and the staging arrays live on this stack frame
+    // Copies are enqueued on the SAME stream as the kernels that read them (the context's streams are
+    // non-blocking: a plain cudaMemcpy on the legacy stream is not ordered against them, and from pageable memory
+    // it may return before the DMA has landed). The stream is drained before the staging arrays go out of scope.
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_model.p, hm, sizeof(hm), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_rates.p, c->rates.data(), sizeof(double) * c->K, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_steps.p, c->steps.data(), sizeof(int32_t) * 4 * n_steps, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_stepoff.p, c->step_off.data(), sizeof(int32_t) * n_steps, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_slotkind.p, c->slot_kind.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_slotoff.p, c->slot_off.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_slotblen.p, c->slot_blen.data(), sizeof(double) * n_slots, cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaStreamSynchronize(s));
-    CUDA_TRY(c, cudaMemcpy(c->d_model.p, hm, sizeof(hm), cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaMemcpy(c->d_rates.p, c->rates.data(), sizeof(double) * c->K, cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaMemcpy(c->d_ops.p, c->ops.data(), sizeof(int32_t) * n_ops, cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaMemcpy(c->d_opblen.p, c->op_blen.data(), sizeof(double) * n_ops, cudaMemcpyHostToDevice));
     PBuildParams pp{};
     pp.eval = c->d_model.as<double>();
     pp.evec = pp.eval + 20;
     pp.ievc = pp.eval + 420;
     pp.rates = c->d_rates.as<double>();
-    pp.ops = c->d_ops.as<int32_t>();
-    pp.op_blen = c->d_opblen.as<double>();
+    pp.slot_kind = c->d_slotkind.as<int32_t>();
+    pp.slot_off = c->d_slotoff.as<int32_t>();
+    pp.slot_blen = c->d_slotblen.as<double>();
     pp.pstream = c->d_pstream.as<double>();
     pp.proot = c->d_proot.as<double>();
+    pp.rate_stride = c->rate_stride;
     pp.root_blen = c->root_blen;
-    pp.n_ops = n_ops;
+    pp.n_slots = n_slots;
     pp.K = c->K;
     prof_begin(c, s, 0, 0);
-    pbuild_kernel<<<dim3(n_ops + 1, c->K), 128, 0, s>>>(pp);
+    pbuild_kernel<<<dim3(n_slots + 1, c->K), 128, 0, s>>>(pp);
     prof_end(c, s);
     CUDA_TRY(c, cudaGetLastError());
     c->p_dirty = false;
     return SR_OK;
 }
 
-template <int M, int NSTAGE>
+template <int M, int NSTAGE, int W>
 int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
-    using Cfg = PruneCfg<M>;
-    const int fixed = NSTAGE * STAGE_BYTES + prune_bar_bytes(NSTAGE);
+    using Cfg = PruneCfg<M, W>;
+    const int fixed = NSTAGE * Cfg::STAGE_BYTES + prune_bar_bytes(NSTAGE);
     int levels = (c->max_smem - fixed) / Cfg::LEVEL_BYTES;
     levels = std::max(0, std::min(levels, c->need_depth));
     const int spill_levels = c->need_depth - levels;
@@ -285,10 +352,10 @@ int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     p.spill_levels = spill_levels;
     p.spill = c->d_spill.as<double>();
     const int smem = fixed + levels * Cfg::LEVEL_BYTES;
-    auto kern = prune_kernel<M, NSTAGE>;
+    auto kern = prune_kernel<M, NSTAGE, W>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prof_begin(c, s, 1, cols);
-    kern<<<grid, PRUNE_THREADS, smem, s>>>(p);
+    kern<<<grid, Cfg::THREADS, smem, s>>>(p);
     prof_end(c, s);
     CUDA_TRY(c, cudaGetLastError());
     return SR_OK;
@@ -300,7 +367,7 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
     if (n <= 0) return SR_OK;
     int rc = ensure_pstream(c, s);
     if (rc) return rc;
-    const int S = (c->tile_m == 4) ? PruneCfg<4>::S : PruneCfg<2>::S;
+    const int S = c->warps * c->tile_m * 8;
     const int64_t col_start = (col_begin / 16) * 16;
     const int64_t skip = col_begin - col_start;
     const int64_t tiles = (skip + n + S - 1) / S;
@@ -309,18 +376,23 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
     CUDA_TRY(c, c->d_rootpart.reserve(sizeof(double) * 2 * (size_t)c->K * ncp * NS));
     CUDA_TRY(c, c->d_rootexp.reserve(sizeof(int32_t) * (size_t)c->K * ncp));
     PruneParams p{};
-    p.ops = c->d_ops.as<int32_t>();
+    p.steps = c->d_steps.as<int4>();
+    p.step_off = c->d_stepoff.as<int32_t>();
     p.pstream = c->d_pstream.as<double>();
+    p.rate_stride = c->rate_stride;
     p.states = d_states;
     p.pitch = pitch;
     p.col0 = col_start;
     p.rootpart = c->d_rootpart.as<double>();
     p.rootexp = c->d_rootexp.as<int32_t>();
     p.ncp = ncp;
-    p.n_ops = (int)c->ops.size();
+    p.n_steps = (int)c->steps.size() / 4;
     p.n_tiles = (int)tiles;
     p.K = c->K;
-    rc = (c->tile_m == 4) ? launch_prune<4, 6>(c, s, p, n) : launch_prune<2, 8>(c, s, p, n);
+    if (c->tile_m == 4) rc = launch_prune<4, 4, 8>(c, s, p, n);
+    else if (c->warps == 15) rc = launch_prune<2, 4, 15>(c, s, p, n);
+    else if (c->warps == 11) rc = launch_prune<2, 4, 11>(c, s, p, n);
+    else rc = launch_prune<2, 4, 8>(c, s, p, n);
     if (rc) return rc;
     RootParams r{};
     r.rootpart = p.rootpart;
@@ -470,9 +542,12 @@ int sr_set_alignment(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* 
     const int64_t dp = ((n_sites + 255) / 256) * 256 + 256;       // row pitch: 16-byte aligned rows + slack for the last tile
     CUDA_TRY(c, c->d_states.reserve((size_t)dp * n_taxa + 512));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    CUDA_TRY(c, cudaMemset(c->d_states.p, SR_STATE_MISSING, (size_t)dp * n_taxa + 512));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_states.p, SR_STATE_MISSING, (size_t)dp * n_taxa + 512, c->stream));
     if (n_sites > 0)
-        CUDA_TRY(c, cudaMemcpy2D(c->d_states.p, dp, states, pitch, n_sites, n_taxa, cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMemcpy2DAsync(c->d_states.p, dp, states, pitch, n_sites, n_taxa, cudaMemcpyHostToDevice, c->stream));
+    sanitize_kernel<<<c->n_sm * 8, 256, 0, c->stream>>>(c->d_states.as<uint4>(), ((size_t)dp * n_taxa + 512) / 16);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->aln_taxa = n_taxa;
     c->aln_sites = n_sites;
     c->aln_pitch = dp;
@@ -579,6 +654,7 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
         if (ci >= 2) cudaStreamWaitEvent(c->s_h2d, sfree_ev[b], 0);     // kernels of chunk ci-2 have consumed states buffer b
         cudaError_t e = cudaMemcpy2DAsync(c->d_chunk_states[b].p, cpitch, states + site0 + done, pitch, m, n_taxa, cudaMemcpyHostToDevice, c->s_h2d);
         if (e != cudaSuccess) { rc = fail(c, SR_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+        sanitize_kernel<<<c->n_sm * 4, 256, 0, c->s_h2d>>>(c->d_chunk_states[b].as<uint4>(), ((size_t)cpitch * n_taxa + 512) / 16);
         cudaEventRecord(up_ev[b], c->s_h2d);
         cudaStreamWaitEvent(c->stream, up_ev[b], 0);
         if (ci >= 2) cudaStreamWaitEvent(c->stream, free_ev[b], 0);     // output buffers b drained
@@ -618,6 +694,12 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     if (k == "tile_m") {
         if (value != 2 && value != 4) return fail(c, SR_ERR_ARG, "tile_m must be 2 or 4");
         c->tile_m = (int)value;
+        c->warps = (value == 4) ? 8 : 11;
+    } else if (k == "warps") {
+        // register files are allocated in 4-warp granules: with the producer warp, 11 and 15 consumers are "free"
+        if (value != 8 && value != 11 && value != 15) return fail(c, SR_ERR_ARG, "warps must be 8, 11 or 15");
+        if (c->tile_m == 4 && value != 8) return fail(c, SR_ERR_ARG, "tile_m 4 supports 8 warps only");
+        c->warps = (int)value;
     } else if (k == "chunk_cols") {
         if (value < 256) return fail(c, SR_ERR_ARG, "chunk_cols must be >= 256");
         c->chunk_cols = (value + 255) / 256 * 256;
@@ -668,9 +750,35 @@ int sr_schedule_info(sr_ctx* c, int64_t* n_steps, int32_t* stack_depth, double* 
     if (!c) return SR_ERR_ARG;
     if (!c->has_tree) return fail(c, SR_ERR_STATE, "tree not set");
     if (c->sched_dirty) { int rc = build_schedule(c); if (rc) return rc; }
-    if (n_steps) *n_steps = (int64_t)c->ops.size();
+    if (n_steps) *n_steps = (int64_t)c->steps.size() / 4;
     if (stack_depth) *stack_depth = c->need_depth;
     if (flops) *flops = 820.0 * (double)c->e_int + 20.0 * (double)c->e_leaf + 1200.0;
+    return SR_OK;
+}
+
+int sr_schedule_dump(int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                     const int32_t* leaf_row, int32_t root, int32_t rescale_every, int64_t cap_steps, int32_t* steps,
+                     int32_t* node_slot, int64_t* n_steps, int32_t* stack_depth) {
+    // host-only: builds the schedule exactly as sr_set_tree does, without touching a GPU
+    if (n_nodes < 3 || !child_off || !child_idx || !blen || !leaf_row || !n_steps) return SR_ERR_ARG;
+    if (root < 0 || root >= n_nodes || child_off[root + 1] - child_off[root] != 2) return SR_ERR_ARG;
+    sr_ctx tmp;
+    tmp.n_nodes = n_nodes;
+    tmp.root = root;
+    tmp.child_off.assign(child_off, child_off + n_nodes + 1);
+    tmp.child_idx.assign(child_idx, child_idx + child_off[n_nodes]);
+    tmp.blen.assign(blen, blen + n_nodes);
+    tmp.leaf_row.assign(leaf_row, leaf_row + n_nodes);
+    tmp.rescale_every = rescale_every > 0 ? rescale_every : 8;
+    int rc = build_schedule(&tmp);
+    if (rc) return rc;
+    *n_steps = (int64_t)tmp.steps.size() / 4;
+    if (stack_depth) *stack_depth = tmp.need_depth;
+    if (steps) {
+        if (*n_steps > cap_steps) return SR_ERR_ARG;
+        memcpy(steps, tmp.steps.data(), sizeof(int32_t) * tmp.steps.size());
+    }
+    if (node_slot) memcpy(node_slot, tmp.node_slot.data(), sizeof(int32_t) * n_nodes);
     return SR_OK;
 }
 
@@ -708,22 +816,25 @@ int sr_debug_pmatrix(sr_ctx* c, int32_t node, int32_t k, double* out) {
     if (k < 0 || k >= c->K || node < 0 || node >= c->n_nodes) return fail(c, SR_ERR_ARG, "node or rate class out of range");
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (node == c->root) {
-        CUDA_TRY(c, cudaMemcpy(out, c->d_proot.as<double>() + (size_t)k * 400, 3200, cudaMemcpyDeviceToHost));
+        CUDA_TRY(c, cudaMemcpyAsync(out, c->d_proot.as<double>() + (size_t)k * 400, 3200, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         return SR_OK;
     }
-    const int op = c->node_op[node];
-    if (op < 0) return fail(c, SR_ERR_ARG, "node %d has no pruning step", node);
-    double slot[SLOT_DOUBLES];
-    CUDA_TRY(c, cudaMemcpy(slot, c->d_pstream.as<double>() + ((size_t)k * c->ops.size() + op) * SLOT_DOUBLES, SLOT_BYTES, cudaMemcpyDeviceToHost));
-    const int code = c->ops[op] & OP_CODE_MASK;
-    if (code >= OP_MV_SET) {
-        for (int e = 0; e < SLOT_DOUBLES; ++e) {
+    const int slot = c->node_slot[node];
+    if (slot < 0) return fail(c, SR_ERR_ARG, "node %d has no pruning step", node);
+    double buf[FRAG_DOUBLES];
+    const bool frag = c->slot_kind[slot] == SLOT_FRAG;
+    CUDA_TRY(c, cudaMemcpyAsync(buf, c->d_pstream.as<double>() + (size_t)k * c->rate_stride + c->slot_off[slot],
+                                frag ? FRAG_BYTES : TABLE_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (frag) {
+        for (int e = 0; e < FRAG_DOUBLES; ++e) {
             const int lane = e & 31, st = e >> 5, s = st / 3, tt = st % 3, g = lane >> 2, q = lane & 3, r = 2 * tt + (g & 1);
-            if (r < 5) out[(5 * (g >> 1) + r) * 20 + 5 * q + s] = slot[e];
+            if (r < 5) out[(5 * (g >> 1) + r) * 20 + 5 * q + s] = buf[e];
         }
     } else {
         for (int s = 0; s < 20; ++s)
-            for (int i = 0; i < 20; ++i) out[i * 20 + s] = slot[s * 20 + i];
+            for (int i = 0; i < 20; ++i) out[i * 20 + s] = buf[s * 20 + i];
     }
     return SR_OK;
 }

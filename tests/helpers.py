@@ -54,3 +54,9 @@ def rel_err(got, want):
     if (~big).any():
         r = max(r, float(np.max(np.abs(got[~big] - want[~big]))))
     return r
+
+
+def lnl_err(got, want):
+    """|delta| / max(1, |lnL|): a log-likelihood near 0 (all-missing column) has no meaningful relative error."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want)))) if got.size else 0.0

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import load_example, rel_err, synthetic
+from helpers import lnl_err, load_example, rel_err, synthetic
 from oracle import oracle
 from subrecon_b200 import native, recon, treeio
 
@@ -190,7 +190,7 @@ def test_polytomy_missing_data_custom_rates(ctx):
         ctx.set_tree(flat)
         ctx.set_alignment(states)
         r = ctx.run()
-        assert rel_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
+        assert lnl_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
     assert abs(r["lnl"][2]) < 1e-9                                       # all-missing column: likelihood 1
 
 
@@ -274,5 +274,6 @@ def test_profile_and_roofline_hooks(ctx, example_problem):
     ctx.set_option("profile", 0)
     assert prof["n_prune"] == 1 and prof["n_root"] == 1 and prof["ms_prune"] > 0 and prof["columns_pruned"] == 130
     info = ctx.schedule_info()
-    assert info["n_steps"] == 34 and info["flops_per_column_rate"] == 55520 / 4      # 55 520 flops/column
+    assert info["n_steps"] == len(native.schedule_dump(p.flat)[0]) < 34              # fused: fewer steps than the 34 edges
+    assert info["flops_per_column_rate"] == 55520 / 4                                 # 55 520 flops/column
     assert 25.0 < ctx.measure_fp64_peak(50) < 45.0

@@ -1,0 +1,144 @@
+"""Host logic of the native path: the fused pruning schedule (subrecon_b200.cu::build_schedule) is executed here by a
+small numpy stack machine with the oracle's matrices and must reproduce the oracle's per-column results. No GPU."""
+import numpy as np
+import pytest
+
+from helpers import load_example, rel_err, synthetic
+from oracle import oracle
+from subrecon_b200 import native, synth, treeio
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    native.build()
+
+
+def run_schedule(p, cols, rescale_every=8):
+    """Interpret the step list exactly as prune_kernel + root_kernel do (same flags, same slot order)."""
+    ft = p.flat
+    steps, node_slot, depth = native.schedule_dump(ft, rescale_every)
+    slot_node = {int(s): v for v, s in enumerate(node_slot) if s >= 0}
+    assert sorted(slot_node) == list(range(len(slot_node)))                    # every edge exactly once, densely numbered
+    rc = ft.child_idx[ft.child_off[ft.root]:ft.child_off[ft.root + 1]]
+    assert len(slot_node) == ft.n_nodes - 1 - sum(1 for v in rc if ft.child_off[v] != ft.child_off[v + 1])
+    m = p.model
+    K = len(p.rates)
+    lnl, joint = [], []
+    for c in cols:
+        tot = np.zeros((20, 20))
+        logs = []
+        per_rate = []
+        for k in range(K):
+            def P_of(v):
+                return oracle.transition_probs(m.Eval, m.Evec, m.Ievc, ft.blen[v] * p.rates[k])
+
+            def tip(v, row):
+                assert ft.leaf_row[v] == row
+                s = p.states[row, c]
+                if v in rc:                                                # tip directly below the root: identity table
+                    return np.ones(20) if s >= 20 else np.eye(20)[s]
+                P = P_of(v)
+                return P.sum(axis=1) if s >= 20 else P[:, s]
+            A, stack, cnt, slot, maxsp = None, [], 0, 0, 0
+            parts = {}
+            for w, r0, r1, r2 in steps:
+                mv, n_pre, post = w & 3, (w >> 2) & 3, (w >> 5) & 1
+                rows = [r0, r1, r2]
+                mv_node = None
+                if mv:
+                    mv_node = slot_node[slot]; slot += 1
+                li = 0
+                for i in range(n_pre):
+                    v = slot_node[slot]; slot += 1
+                    t = tip(v, rows[li]); li += 1
+                    A = t if (i == 0 and (w & 16)) else A * t
+                if mv:
+                    A = P_of(mv_node) @ A
+                    if mv == 2:
+                        A = A * stack.pop()
+                    if post:
+                        v = slot_node[slot]; slot += 1
+                        A = A * tip(v, rows[li])
+                else:
+                    assert not post
+                if w & 64:
+                    e = int(np.floor(np.log2(A.max())))
+                    A = A * 2.0 ** (-e)
+                    cnt += e
+                if w & 128:
+                    stack.append(A)
+                    maxsp = max(maxsp, len(stack))
+                if w & 256:
+                    parts[0] = A
+                if w & 512:
+                    parts[1] = A
+            assert not stack and slot == len(slot_node) and maxsp <= depth
+            a, b = rc
+            Pr = oracle.transition_probs(m.Eval, m.Evec, m.Ievc, (ft.blen[a] + ft.blen[b]) * p.rates[k])
+            per_rate.append((m.pi * parts[0])[:, None] * Pr * parts[1][None, :])
+            logs.append(cnt)
+        emax = max(logs)
+        for k in range(K):
+            tot += per_rate[k] * 2.0 ** (logs[k] - emax)
+        lnl.append(np.log(tot.sum()) + emax * np.log(2.0) - np.log(K))
+        joint.append(tot / tot.sum())
+    return np.array(lnl), np.array(joint), steps, depth
+
+
+def test_schedule_on_example(example_problem):
+    p = example_problem
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
+    cols = [0, 13, 40, 129]
+    got_l, got_j, steps, depth = run_schedule(p, cols)
+    assert rel_err(got_l, lnl[cols]) < 1e-12 and rel_err(got_j, joint[cols]) < 1e-9
+    assert depth == 2 and len(steps) < 34                       # fused: fewer steps than the 34 edges
+    mv_steps = int(np.count_nonzero(steps[:, 0] & 3))
+    assert mv_steps == 15                                       # one MV per internal edge below the root children (E_int = N-4)
+
+
+def test_schedule_shapes():
+    class P:
+        pass
+    model = oracle.OracleModel("JTT")
+    rates = np.array([0.4, 1.6])
+    newicks = [
+        "((a:0.1,b:0.2):0.1,(c:0.1,d:0.3):0.2);",                                        # two cherries
+        "((a:0.2,b:0.01,f:0.3,(g:0.1,h:0.2):0.0,i:0.1,j:0.2,k:0.3):0.1,(c:0.3,d:0.05,e:0.6):0.02);",   # polytomies
+        "(a:0.1,(b:0.2,c:0.3):0.1);",                                                    # tip as root child
+        "(((a:0.1,b:0.1):0.1,(c:0.1,d:0.1):0.1):0.1,((e:0.1,f:0.1):0.1,((g:0.1,h:0.1):0.1,(i:0.2,j:0.3):0.1):0.1):0.1);",
+    ]
+    for nw in newicks:
+        tree = treeio.parse_newick(nw)
+        p = P()
+        p.flat = treeio.flatten_tree(tree)
+        n_tips = len(tree.leaves())
+        rng = np.random.default_rng(7)
+        p.states = rng.integers(0, 21, size=(n_tips, 6)).astype(np.uint8)
+        p.states[p.states == 20] = 255
+        p.model, p.rates = model, rates
+        if "(a:0.1,(b" in nw:
+            rates1 = np.array([1.0])
+            p.rates = rates1                                   # the reference only handles this shape for K = 1
+        lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
+        got_l, got_j, steps, depth = run_schedule(p, range(6))
+        assert rel_err(got_l, lnl) < 1e-12 and rel_err(got_j, joint) < 1e-9, nw
+        got_l, got_j, _, _ = run_schedule(p, range(2), rescale_every=1)
+        assert rel_err(got_l, lnl[:2]) < 1e-12
+
+
+@pytest.mark.parametrize("kind,n,depth_max", [("balanced", 64, 5), ("yule", 200, 6), ("caterpillar", 300, 0)])
+def test_schedule_synthetic(kind, n, depth_max):
+    class P:
+        pass
+    tree = {"balanced": synth.balanced_tree, "yule": synth.yule_tree, "caterpillar": synth.caterpillar_tree}[kind](n, seed=5)
+    p = P()
+    p.flat = treeio.flatten_tree(tree)
+    p.model = oracle.OracleModel("WAG")
+    p.rates = oracle.gamma_rates(2, 0.5)
+    p.states = synth.simulate_alignment(tree, p.model, p.rates, 3, seed=9)
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
+    got_l, got_j, steps, depth = run_schedule(p, range(3))
+    assert rel_err(got_l, lnl) < 1e-12 and rel_err(got_j, joint) < 1e-9
+    assert depth <= depth_max
+    n_mv = int(np.count_nonzero(steps[:, 0] & 3))
+    assert len(steps) <= n_mv + 4 + (0 if kind != "balanced" else n // 2)      # nearly every step carries an MMA burst
