@@ -106,8 +106,10 @@ int sr_run_streamed(sr_ctx *ctx, int32_t n_taxa, int64_t n_sites, const uint8_t 
 void *sr_host_alloc(size_t bytes);
 void sr_host_free(void *p);
 
-/* Tuning / introspection. Options: "tile_m" (MMA column tiles per warp: 2 or 4), "chunk_cols"
- * (columns per pipeline chunk), "profile" (0/1: record per-kernel events), "rescale_every" (edges). */
+/* Tuning / introspection. Options: "tile_m" (MMA column tiles per warp: 2 or 4), "warps" (consumer warps per
+ * CTA: 8, 11 or 15), "holes" (0..2 pauses inside a warp's MMA burst), "rotate" (0/1 burst hand-off between the warps of
+ * an SM sub-partition), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage), "profile"
+ * (0/1: record per-kernel events), "rescale_every" (edges between power-of-two rescalings). */
 int sr_set_option(sr_ctx *ctx, const char *name, int64_t value);
 int sr_get_profile(sr_ctx *ctx, sr_profile *out);     /* synchronises the context's streams */
 int sr_profile_reset(sr_ctx *ctx);

@@ -25,8 +25,9 @@
 namespace srk {
 
 constexpr int NS = 20;
-constexpr int FRAG_DOUBLES = 480;                 // a 20x20 matrix as 15 DMMA B-fragments x 32 lanes (padded to 24 rows)
-constexpr int FRAG_BYTES = FRAG_DOUBLES * 8;      // 3840
+constexpr int FRAG_DOUBLES = 512;                 // a 20x20 matrix as 15 (+1 pad) DMMA B-fragments x 32 lanes, stored as
+                                                  // 8 pairs x 32 lanes x 2 doubles so a lane fetches two fragments per LDS.128
+constexpr int FRAG_BYTES = FRAG_DOUBLES * 8;      // 4096
 constexpr int TABLE_DOUBLES = 21 * NS;            // P^T rows for states 0..19 + the missing-data row
 constexpr int TABLE_BYTES = TABLE_DOUBLES * 8;    // 3360
 
@@ -70,8 +71,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 // FP64 tensor-core MMA, D(8x8) += A(8x4) · B(4x8)   (SASS: DMMA.8x8x4)
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // ------------------------------------------------------------------------------------------- K1
@@ -124,12 +125,16 @@ __global__ void __launch_bounds__(128) pbuild_kernel(PBuildParams p) {
     }
     double* out = p.pstream + (size_t)k * p.rate_stride + p.slot_off[slot];
     if (kind == SLOT_FRAG) {
-        // B-fragments: (s*3+t)*32 + lane = P[5(g/2) + 2t + (g&1)][5q + s], g = lane>>2, q = lane&3
+        // B-fragment f = s*3+t of lane (g = lane>>2, q = lane&3) is P[5(g/2) + 2t + (g&1)][5q + s]; it is stored at
+        // ((f>>1)*32 + lane)*2 + (f&1)
         for (int e = tid; e < FRAG_DOUBLES; e += 128) {
-            const int lane = e & 31, st = e >> 5, s = st / 3, tt = st % 3;
-            const int g = lane >> 2, q = lane & 3;
-            const int r = 2 * tt + (g & 1);
-            out[e] = (r < 5) ? P[(5 * (g >> 1) + r) * NS + 5 * q + s] : 0.0;
+            const int half = e & 1, lane = (e >> 1) & 31, f = ((e >> 6) << 1) | half;
+            double v = 0.0;
+            if (f < 15) {
+                const int s = f / 3, tt = f % 3, g = lane >> 2, q = lane & 3, r = 2 * tt + (g & 1);
+                if (r < 5) v = P[(5 * (g >> 1) + r) * NS + 5 * q + s];
+            }
+            out[e] = v;
         }
     } else {
         // gather table T[s][i] = P[i][s]; row 20 = Σ_j P[i][j] (a missing tip is the all-ones vector,
@@ -214,7 +219,13 @@ struct PruneCfg {
 
 __host__ __device__ constexpr int prune_bar_bytes(int nstage) { return ((2 * nstage * 8 + 127) / 128) * 128; }
 
-template <int M, int NSTAGE, int W_>
+// Named-barrier hand-off between the consumer warps of one SM sub-partition (warp id mod 4): a warp may start its MMA
+// burst only when the previous warp in the rotation has issued its last DMMA. Without it, two warps that burst at the
+// same time interleave, finish together, do their non-MMA work together and leave the tensor pipe idle together.
+__device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false>
 __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) {
     using Cfg = PruneCfg<M, W_>;
     constexpr int W = Cfg::W;
@@ -268,6 +279,13 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
     double* spill_base = p.spill + ((size_t)blockIdx.x * W + warp) * (size_t)p.spill_levels * TILE_DOUBLES;
     double* my_stack = stack + warp * TILE_DOUBLES + lane;
     const int st_lane_off = Cfg::STATES_OFF + warp * (M * 8) + g;
+    // rotation bookkeeping: sub-partition sp4 = warp & 3 holds warps sp4, sp4+4, ...; position rpos among n_rot of them
+    const int sp4 = warp & 3, rpos = warp >> 2;
+    const int n_rot = (W - sp4 + 3) / 4;
+    // ids 0..15: barrier 0 is only used by the one __syncthreads() above, before any hand-off
+    const int bar_wait_id = sp4 * 4 + (rpos + n_rot - 1) % n_rot;         // armed by the previous warp in the rotation
+    const int bar_pass_id = sp4 * 4 + rpos;
+    bool first_burst = (rpos == 0);
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int k = item / p.n_tiles, tile = item - k * p.n_tiles;
@@ -281,6 +299,7 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
         }
         int sp = 0;
         int w_next = __ldg(&p.steps[0].x);
+        bool next_ready = false;           // result of an early, non-blocking probe of the next stage's full barrier
         for (int step = 0; step < p.n_steps; ++step, ++it) {
             const int stage = it % NSTAGE;
             const uint32_t ph = (it / NSTAGE) & 1;
@@ -288,19 +307,24 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
             if (step + 1 < p.n_steps) w_next = __ldg(&p.steps[step + 1].x);
             const int mv = w & ST_MV_MASK, n_pre = (w >> ST_NPRE_SHIFT) & 3;
             const unsigned char* stg = stages + stage * STAGE_BYTES;
-            const double* frag = reinterpret_cast<const double*>(stg) + lane;
+            const double2* frag = reinterpret_cast<const double2*>(stg) + lane;
             const double* tab = reinterpret_cast<const double*>(stg + (mv ? FRAG_BYTES : 0)) + q * 5;
             const unsigned char* stb = stg + st_lane_off;
-            mbar_wait(&full[stage], ph);
+            if (!next_ready) mbar_wait(&full[stage], ph);
+            next_ready = false;
 
             // ---- all shared-memory reads of the step are issued up front
             int s0[M], s1[M], s2[M];
 #pragma unroll
             for (int j = 0; j < M; ++j) { s0[j] = stb[j * 8]; s1[j] = stb[S + j * 8]; s2[j] = stb[2 * S + j * 8]; }
-            double Bf[15];
+            // The burst is issued in HOLES+1 chunks; the fragments of chunk c+1 are loaded only after chunk c was issued,
+            // so the warp pauses for one LDS latency inside its own burst. Sibling warps' Hadamard DMULs (same FP64 pipe)
+            // slip into those holes instead of starving until the whole burst is over (which bunches the warps).
+            double Bf[16];
+            constexpr int FIRST = (HOLES == 0) ? 8 : (HOLES == 1 ? 5 : 3);      // fragment pairs fetched before the burst
             if (mv) {
 #pragma unroll
-                for (int i = 0; i < 15; ++i) Bf[i] = frag[i * 32];
+                for (int i = 0; i < FIRST; ++i) { const double2 v = frag[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
             }
             constexpr bool LAZY = (M >= 4);      // big tiles: fetch the post-MMA operands after the burst (registers)
             double pv[M][5];
@@ -320,13 +344,14 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
                         for (int r = 0; r < 5; ++r) pv[j][r] = __ldcg(src + (j * 5 + r) * 32);
                 }
             }
-            // ---- tips below this node (gathers of P^T rows by observed state)
+            // ---- tips below this node (gathers of P^T rows by observed state): loads first ...
+            double tp0[M][5], tp1[M][5];
             if (n_pre >= 1) {
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
                     const double* row = tab + s0[j] * NS;
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) A[j][r] = (w & ST_PRE0_SET) ? row[r] : A[j][r] * row[r];
+                    for (int r = 0; r < 5; ++r) tp0[j][r] = row[r];
                 }
             }
             if (n_pre == 2) {
@@ -334,31 +359,62 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
                 for (int j = 0; j < M; ++j) {
                     const double* row = tab + TABLE_DOUBLES + s1[j] * NS;
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) A[j][r] *= row[r];
+                    for (int r = 0; r < 5; ++r) tp1[j][r] = row[r];
                 }
             }
-            if (mv) {
-                double vp[M][5];
-                if ((w & ST_NPOST) && !LAZY) {
+            double vp[M][5];
+            if (mv && (w & ST_NPOST) && !LAZY) {
 #pragma unroll
-                    for (int j = 0; j < M; ++j) {
-                        const int sx = n_pre == 0 ? s0[j] : (n_pre == 1 ? s1[j] : s2[j]);
-                        const double* row = tab + n_pre * TABLE_DOUBLES + sx * NS;
+                for (int j = 0; j < M; ++j) {
+                    const int sx = n_pre == 0 ? s0[j] : (n_pre == 1 ? s1[j] : s2[j]);
+                    const double* row = tab + n_pre * TABLE_DOUBLES + sx * NS;
 #pragma unroll
-                        for (int r = 0; r < 5; ++r) vp[j][r] = row[r];
-                    }
+                    for (int r = 0; r < 5; ++r) vp[j][r] = row[r];
                 }
+            }
+            // ... products after all of them are in flight
+            if (n_pre >= 1) {
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) A[j][r] = (w & ST_PRE0_SET) ? tp0[j][r] : A[j][r] * tp0[j][r];
+            }
+            if (n_pre == 2) {
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) A[j][r] *= tp1[j][r];
+            }
+            if (mv) {
                 double acc[M][3][2];
 #pragma unroll
                 for (int j = 0; j < M; ++j)
 #pragma unroll
                     for (int t = 0; t < 3; ++t) { acc[j][t][0] = 0.0; acc[j][t][1] = 0.0; }
+                if (ROT && n_rot > 1) {          // rotation: burst only after the previous warp of this sub-partition issued its last DMMA
+                    if (!first_burst) bar_sync64(bar_wait_id);
+                    first_burst = false;
+                }
 #pragma unroll
-                for (int s = 0; s < 5; ++s)
+                for (int s = 0; s < 5; ++s) {
+                    // HOLES == 1: pairs 5..7 (fragments 10..15) before s = 3 (uses 9..11: fragment 9 came with pair 4)
+                    // HOLES == 2: pairs 3..5 before s = 2 (fragments 6..11), pairs 6..7 before s = 4 (12..14)
+                    if ((HOLES == 1 && s == 3) || (HOLES == 2 && (s == 2 || s == 4))) {
+                        asm volatile("" ::: "memory");
+                        const int lo = (HOLES == 1) ? 5 : (s == 2 ? 3 : 6), hi = (HOLES == 2 && s == 2) ? 6 : 8;
+#pragma unroll
+                        for (int i = lo; i < hi; ++i) { const double2 v = frag[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
+                    }
 #pragma unroll
                     for (int j = 0; j < M; ++j)
 #pragma unroll
                         for (int t = 0; t < 3; ++t) dmma(acc[j][t][0], acc[j][t][1], A[j][s], Bf[s * 3 + t]);
+                }
+                if (ROT && n_rot > 1) bar_arrive64(bar_pass_id);
+                {   // probe the next stage now: the ~60-cycle TRYWAIT latency hides behind this step's epilogue
+                    const uint32_t itn = it + 1;
+                    next_ready = mbar_try_wait(&full[itn % NSTAGE], (itn / NSTAGE) & 1);
+                }
                 if (LAZY) {
                     if (w & ST_NPOST) {
 #pragma unroll
@@ -385,7 +441,10 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
                         }
                     }
                 }
-                if (!LAZY) stage_release(&empty[stage], lane);   // every operand of the step left shared memory before the burst
+                if (!LAZY) {      // every read of the stage was issued before (or inside) the burst and its value has been
+                    __syncwarp(); // consumed by an issued DMMA/DMUL or sits in a register: nothing left for the TMA to race
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+                }
 #pragma unroll
                 for (int j = 0; j < M; ++j)
 #pragma unroll

@@ -70,6 +70,8 @@ struct sr_ctx {
 
     // options
     int tile_m = 2;
+    int holes = 2;                      // pauses inside a warp's MMA burst (0..2), see kernels.cuh
+    int rotate = 1;                     // named-barrier burst rotation among the warps of an SM sub-partition
     int warps = 11;                     // consumer warps per CTA (tile_m == 2 only: 8, 11 or 15)
     int64_t chunk_cols = 1 << 20;       // resident runs: columns per launch
     int64_t stream_chunk_cols = 1 << 17; // streamed runs: columns per pipeline stage (H2D | kernels | D2H overlap)
@@ -337,7 +339,7 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     return SR_OK;
 }
 
-template <int M, int NSTAGE, int W>
+template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false>
 int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     using Cfg = PruneCfg<M, W>;
     const int fixed = NSTAGE * Cfg::STAGE_BYTES + prune_bar_bytes(NSTAGE);
@@ -352,7 +354,7 @@ int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     p.spill_levels = spill_levels;
     p.spill = c->d_spill.as<double>();
     const int smem = fixed + levels * Cfg::LEVEL_BYTES;
-    auto kern = prune_kernel<M, NSTAGE, W>;
+    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prof_begin(c, s, 1, cols);
     kern<<<grid, Cfg::THREADS, smem, s>>>(p);
@@ -389,10 +391,15 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
     p.n_steps = (int)c->steps.size() / 4;
     p.n_tiles = (int)tiles;
     p.K = c->K;
+    // kernel variants: tile_m (column tiles per warp), consumer warps, holes in the MMA burst, burst rotation
+    const int hl = c->holes, rot = c->rotate;
     if (c->tile_m == 4) rc = launch_prune<4, 4, 8>(c, s, p, n);
-    else if (c->warps == 15) rc = launch_prune<2, 4, 15>(c, s, p, n);
-    else if (c->warps == 11) rc = launch_prune<2, 4, 11>(c, s, p, n);
-    else rc = launch_prune<2, 4, 8>(c, s, p, n);
+    else if (c->warps == 8) rc = rot ? launch_prune<2, 4, 8, 2, true>(c, s, p, n) : launch_prune<2, 4, 8, 0, false>(c, s, p, n);
+    else if (c->warps == 15) rc = rot ? launch_prune<2, 4, 15, 2, true>(c, s, p, n) : launch_prune<2, 4, 15, 0, false>(c, s, p, n);
+    else if (rot) rc = (hl == 0) ? launch_prune<2, 4, 11, 0, true>(c, s, p, n)
+                     : (hl == 1) ? launch_prune<2, 4, 11, 1, true>(c, s, p, n) : launch_prune<2, 4, 11, 2, true>(c, s, p, n);
+    else rc = (hl == 0) ? launch_prune<2, 4, 11, 0, false>(c, s, p, n)
+            : (hl == 1) ? launch_prune<2, 4, 11, 1, false>(c, s, p, n) : launch_prune<2, 4, 11, 2, false>(c, s, p, n);
     if (rc) return rc;
     RootParams r{};
     r.rootpart = p.rootpart;
@@ -703,6 +710,11 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     } else if (k == "chunk_cols") {
         if (value < 256) return fail(c, SR_ERR_ARG, "chunk_cols must be >= 256");
         c->chunk_cols = (value + 255) / 256 * 256;
+    } else if (k == "holes") {
+        if (value < 0 || value > 2) return fail(c, SR_ERR_ARG, "holes must be 0, 1 or 2");
+        c->holes = (int)value;
+    } else if (k == "rotate") {
+        c->rotate = value != 0;
     } else if (k == "stream_chunk_cols") {
         if (value < 256) return fail(c, SR_ERR_ARG, "stream_chunk_cols must be >= 256");
         c->stream_chunk_cols = (value + 255) / 256 * 256;
@@ -829,7 +841,9 @@ int sr_debug_pmatrix(sr_ctx* c, int32_t node, int32_t k, double* out) {
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (frag) {
         for (int e = 0; e < FRAG_DOUBLES; ++e) {
-            const int lane = e & 31, st = e >> 5, s = st / 3, tt = st % 3, g = lane >> 2, q = lane & 3, r = 2 * tt + (g & 1);
+            const int half = e & 1, lane = (e >> 1) & 31, f = ((e >> 6) << 1) | half;
+            if (f >= 15) continue;
+            const int s = f / 3, tt = f % 3, g = lane >> 2, q = lane & 3, r = 2 * tt + (g & 1);
             if (r < 5) out[(5 * (g >> 1) + r) * 20 + 5 * q + s] = buf[e];
         }
     } else {

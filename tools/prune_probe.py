@@ -15,6 +15,8 @@ ap.add_argument("--cols", type=int, default=131072)
 ap.add_argument("--tile-m", type=int, default=2)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--warps", type=int, default=0)
+ap.add_argument("--holes", type=int, default=-1)
+ap.add_argument("--rotate", type=int, default=-1)
 ap.add_argument("--taxa", type=int, default=1000)
 ap.add_argument("--tree", default="yule")
 ap.add_argument("--ncat", type=int, default=4)
@@ -31,6 +33,10 @@ else:
 states = np.tile(base, (1, (a.cols + 4095) // 4096))[:, :a.cols]
 ctx = native.Context(0)
 ctx.set_option("tile_m", a.tile_m)
+if a.holes >= 0:
+    ctx.set_option("holes", a.holes)
+if a.rotate >= 0:
+    ctx.set_option("rotate", a.rotate)
 if a.warps:
     ctx.set_option("warps", a.warps)
 ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
@@ -46,5 +52,5 @@ for _ in range(a.reps):
 p = ctx.profile(reset=True)
 ms = p["ms_prune"] / p["n_prune"]
 tf = info["flops_per_column_rate"] * len(rates) * a.cols / ms * 1e-9
-print(f"tree={a.tree} taxa={a.taxa} cols={a.cols} tile_m={a.tile_m} warps={a.warps} K={a.ncat} depth={info['stack_depth']} steps={info['n_steps']}: "
+print(f"tree={a.tree} taxa={a.taxa} cols={a.cols} tile_m={a.tile_m} warps={a.warps} holes={a.holes} rotate={a.rotate} K={a.ncat} depth={info['stack_depth']} steps={info['n_steps']}: "
       f"prune {ms:.3f} ms/launch  {a.cols / ms * 1e-3:.3f} Mcol/s  {tf:.2f} TFLOP/s  root {p['ms_root'] / p['n_root']:.3f} ms")
