@@ -104,6 +104,30 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank (and therefore its page-locked buffers, first touch) to the NUMA node its GPU hangs off."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_run(a, columns, threads, mode, flat, model_name, rates, states):
     """Time the oracle (the CPU restatement of the reference's per-column task) on `columns` columns."""
     from oracle import oracle
@@ -158,8 +182,10 @@ def run_b200(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product arm has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -259,17 +285,55 @@ def run_b200(a):
                "bit_identical_to_resident": bool(np.array_equal(h_lnl.array, d_lnl.cpu().numpy())) and
                                             bool(np.array_equal(h_joint.array[:4096].reshape(-1, 400), d_joint[:4096].cpu().numpy()))}
 
+    # ---- e2e, compact result: what the reference's SiteResult keeps per column (lnL, maxII, max, entries >= threshold;
+    #      recon/SiteResult.java:55,69-83) at the default -threshold 0.5 — 112 B instead of 3 208 B per column back to the host
+    e2e_compact = None
+    if not a.no_e2e:
+        h_comp = native.PinnedArray(L, native.COMPACT_DTYPE)
+        outc = {"lnl": h_lnl.array, "compact": h_comp.array}
+
+        def step_e2e_compact():
+            ctx.set_rates(rates)
+            ctx.run_streamed(h_states.array, 0, L, want_joint=False, want_compact=True, threshold=0.5, out=outc)
+
+        step_e2e_compact()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            step_e2e_compact()
+        torch.cuda.synchronize()
+        dtc = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e_compact = {"value": world * L * a.steps / dtc, "unit": UNIT, "h2d_bytes_per_step": int(N) * L,
+                       "d2h_bytes_per_step": L * (8 + native.COMPACT_DTYPE.itemsize), "ms_per_step": dtc / a.steps * 1e3,
+                       "lnl_identical_to_full": bool(np.array_equal(h_comp.array["lnl"], d_lnl.cpu().numpy()))}
+
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (same launch size), else null
+    traffic = None
+    try:
+        if (a.taxa, a.columns, a.ncat, a.model) == (1000, 1_000_000, 4, "wag"):
+            prof_json = json.load(open(os.path.join(ROOT, "profiles", "r01_prune_kernel_final_ncu_full_1Mcols.json")))
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            traffic = sum(float(prof_json[k]["value"]) * scale[prof_json[k]["unit"]]
+                          for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        traffic = None
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": None,
+                         "frac": achieved / peak_tflops, "traffic": traffic,
+                         "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of prune_kernel from "
+                                         "profiles/r01_prune_kernel_final_ncu_full_1Mcols.json; the kernel's own HBM need is "
+                                         "K*N bytes of states in + K*328 bytes of root partials out per column = 5.3 GB per launch "
+                                         "(0.5 % of the HBM roof: the path is FP64-tensor-bound, not HBM-bound)",
                          "kernel": "prune_kernel (FP64 DMMA m8n8k4)", "kernel_ms": k2_ms,
                          "kernel_share_of_step": prof["ms_prune"] / ms if world == 1 else None,
                          "flops_per_column": flops_per_col,
                          "peak_source": "live DMMA probe (sr_measure_fp64_peak) on this GPU; MEASURED_PEAKS.json has no FP64 entry; "
                                         "nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s"},
-            "e2e": e2e, "gpu_launches": launches,
+            "e2e": e2e, "e2e_compact": e2e_compact, "numa_node": numa_node, "gpu_launches": launches,
             "kernel_ms": {"pbuild": prof["ms_pbuild"] / max(1, prof["n_pbuild"]), "prune": k2_ms,
                           "root": prof["ms_root"] / max(1, prof["n_root"])},
             "clocks": clocks, "total_lnl": total_lnl,
