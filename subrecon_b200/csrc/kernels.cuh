@@ -225,7 +225,7 @@ __host__ __device__ constexpr int prune_bar_bytes(int nstage) { return ((2 * nst
 __device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false>
+template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false, bool PREF = false>
 __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) {
     using Cfg = PruneCfg<M, W_>;
     constexpr int W = Cfg::W;
@@ -299,30 +299,55 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
         }
         int sp = 0;
         int w_next = __ldg(&p.steps[0].x);
-        bool next_ready = false;           // result of an early, non-blocking probe of the next stage's full barrier
+        bool next_ready = false;           // result of an early, non-blocking probe of a later stage's full barrier
+        static_assert(!PREF || HOLES == 2, "cross-step prefetch rides on the first hole of the burst");
+        constexpr int FIRST = (HOLES == 0) ? 8 : (HOLES == 1 ? 5 : 3);      // fragment pairs fetched before the burst
+        int s0[M], s1[M], s2[M];
+        double Bf[16];
+        if (PREF) {
+            // prologue of the work item: the operands every later step gets from its predecessor's burst hole
+            const int stage0 = it % NSTAGE;
+            mbar_wait(&full[stage0], (it / NSTAGE) & 1);
+            const unsigned char* stg0 = stages + stage0 * STAGE_BYTES;
+            const unsigned char* stb0 = stg0 + st_lane_off;
+            const double2* frag0 = reinterpret_cast<const double2*>(stg0) + lane;
+#pragma unroll
+            for (int j = 0; j < M; ++j) { s0[j] = stb0[j * 8]; s1[j] = stb0[S + j * 8]; s2[j] = stb0[2 * S + j * 8]; }
+#pragma unroll
+            for (int i = 0; i < FIRST; ++i) { const double2 v = frag0[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
+        }
         for (int step = 0; step < p.n_steps; ++step, ++it) {
             const int stage = it % NSTAGE;
             const uint32_t ph = (it / NSTAGE) & 1;
             const int w = w_next;
-            if (step + 1 < p.n_steps) w_next = __ldg(&p.steps[step + 1].x);
+            const bool has_next = step + 1 < p.n_steps;
+            if (has_next) w_next = __ldg(&p.steps[step + 1].x);
             const int mv = w & ST_MV_MASK, n_pre = (w >> ST_NPRE_SHIFT) & 3;
             const unsigned char* stg = stages + stage * STAGE_BYTES;
             const double2* frag = reinterpret_cast<const double2*>(stg) + lane;
             const double* tab = reinterpret_cast<const double*>(stg + (mv ? FRAG_BYTES : 0)) + q * 5;
             const unsigned char* stb = stg + st_lane_off;
-            if (!next_ready) mbar_wait(&full[stage], ph);
+            // PREF: this step's stage was already waited for (by the predecessor or the prologue); make sure the NEXT
+            // one has landed before the burst, because its first operands are fetched inside the burst
+            const uint32_t itn = it + 1;
+            const unsigned char* stgn = stages + (itn % NSTAGE) * STAGE_BYTES;
+            int sn0[M], sn1[M], sn2[M];
+            if (PREF) {
+                if (has_next && !next_ready) mbar_wait(&full[itn % NSTAGE], (itn / NSTAGE) & 1);
+            } else {
+                if (!next_ready) mbar_wait(&full[stage], ph);
+            }
             next_ready = false;
 
             // ---- all shared-memory reads of the step are issued up front
-            int s0[M], s1[M], s2[M];
+            if (!PREF) {
 #pragma unroll
-            for (int j = 0; j < M; ++j) { s0[j] = stb[j * 8]; s1[j] = stb[S + j * 8]; s2[j] = stb[2 * S + j * 8]; }
+                for (int j = 0; j < M; ++j) { s0[j] = stb[j * 8]; s1[j] = stb[S + j * 8]; s2[j] = stb[2 * S + j * 8]; }
+            }
             // The burst is issued in HOLES+1 chunks; the fragments of chunk c+1 are loaded only after chunk c was issued,
             // so the warp pauses for one LDS latency inside its own burst. Sibling warps' Hadamard DMULs (same FP64 pipe)
             // slip into those holes instead of starving until the whole burst is over (which bunches the warps).
-            double Bf[16];
-            constexpr int FIRST = (HOLES == 0) ? 8 : (HOLES == 1 ? 5 : 3);      // fragment pairs fetched before the burst
-            if (mv) {
+            if (mv && !PREF) {
 #pragma unroll
                 for (int i = 0; i < FIRST; ++i) { const double2 v = frag[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
             }
@@ -404,6 +429,15 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
                         const int lo = (HOLES == 1) ? 5 : (s == 2 ? 3 : 6), hi = (HOLES == 2 && s == 2) ? 6 : 8;
 #pragma unroll
                         for (int i = lo; i < hi; ++i) { const double2 v = frag[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
+                        if (PREF && s == 2 && has_next) {
+                            // fragments 0..5 are dead (k-steps 0,1 issued): refill them, and the tip state codes, for step+1
+                            const double2* fragn = reinterpret_cast<const double2*>(stgn) + lane;
+                            const unsigned char* stbn = stgn + st_lane_off;
+#pragma unroll
+                            for (int i = 0; i < FIRST; ++i) { const double2 v = fragn[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
+#pragma unroll
+                            for (int j = 0; j < M; ++j) { sn0[j] = stbn[j * 8]; sn1[j] = stbn[S + j * 8]; sn2[j] = stbn[2 * S + j * 8]; }
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < M; ++j)
@@ -412,8 +446,8 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
                 }
                 if (ROT && n_rot > 1) bar_arrive64(bar_pass_id);
                 {   // probe the next stage now: the ~60-cycle TRYWAIT latency hides behind this step's epilogue
-                    const uint32_t itn = it + 1;
-                    next_ready = mbar_try_wait(&full[itn % NSTAGE], (itn / NSTAGE) & 1);
+                    const uint32_t itp = it + (PREF ? 2 : 1);
+                    next_ready = mbar_try_wait(&full[itp % NSTAGE], (itp / NSTAGE) & 1);
                 }
                 if (LAZY) {
                     if (w & ST_NPOST) {
@@ -472,6 +506,18 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
                 }
             } else {
                 stage_release(&empty[stage], lane);
+                if (PREF && has_next) {          // no burst to hide behind: fetch the next step's first operands here
+                    const double2* fragn = reinterpret_cast<const double2*>(stgn) + lane;
+                    const unsigned char* stbn = stgn + st_lane_off;
+#pragma unroll
+                    for (int i = 0; i < FIRST; ++i) { const double2 v = fragn[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
+#pragma unroll
+                    for (int j = 0; j < M; ++j) { sn0[j] = stbn[j * 8]; sn1[j] = stbn[S + j * 8]; sn2[j] = stbn[2 * S + j * 8]; }
+                }
+            }
+            if (PREF && has_next) {
+#pragma unroll
+                for (int j = 0; j < M; ++j) { s0[j] = sn0[j]; s1[j] = sn1[j]; s2[j] = sn2[j]; }
             }
             if (w & STF_ANY) {
                 if (w & STF_RESCALE) {

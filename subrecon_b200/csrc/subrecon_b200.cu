@@ -71,6 +71,7 @@ struct sr_ctx {
     // options
     int tile_m = 2;
     int holes = 2;                      // pauses inside a warp's MMA burst (0..2), see kernels.cuh
+    int prefetch = 0;                   // fetch the next step's first operands inside the current MMA burst
     int rotate = 1;                     // named-barrier burst rotation among the warps of an SM sub-partition
     int warps = 11;                     // consumer warps per CTA (tile_m == 2 only: 8, 11 or 15)
     int64_t chunk_cols = 1 << 20;       // resident runs: columns per launch
@@ -339,7 +340,7 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     return SR_OK;
 }
 
-template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false>
+template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false, bool PREF = false>
 int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     using Cfg = PruneCfg<M, W>;
     const int fixed = NSTAGE * Cfg::STAGE_BYTES + prune_bar_bytes(NSTAGE);
@@ -354,7 +355,7 @@ int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     p.spill_levels = spill_levels;
     p.spill = c->d_spill.as<double>();
     const int smem = fixed + levels * Cfg::LEVEL_BYTES;
-    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT>;
+    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT, PREF>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prof_begin(c, s, 1, cols);
     kern<<<grid, Cfg::THREADS, smem, s>>>(p);
@@ -396,6 +397,8 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
     if (c->tile_m == 4) rc = launch_prune<4, 4, 8>(c, s, p, n);
     else if (c->warps == 8) rc = rot ? launch_prune<2, 4, 8, 2, true>(c, s, p, n) : launch_prune<2, 4, 8, 0, false>(c, s, p, n);
     else if (c->warps == 15) rc = rot ? launch_prune<2, 4, 15, 2, true>(c, s, p, n) : launch_prune<2, 4, 15, 0, false>(c, s, p, n);
+    else if (c->prefetch && rot) rc = launch_prune<2, 4, 11, 2, true, true>(c, s, p, n);
+    else if (c->prefetch) rc = launch_prune<2, 4, 11, 2, false, true>(c, s, p, n);
     else if (rot) rc = (hl == 0) ? launch_prune<2, 4, 11, 0, true>(c, s, p, n)
                      : (hl == 1) ? launch_prune<2, 4, 11, 1, true>(c, s, p, n) : launch_prune<2, 4, 11, 2, true>(c, s, p, n);
     else rc = (hl == 0) ? launch_prune<2, 4, 11, 0, false>(c, s, p, n)
@@ -713,6 +716,8 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     } else if (k == "holes") {
         if (value < 0 || value > 2) return fail(c, SR_ERR_ARG, "holes must be 0, 1 or 2");
         c->holes = (int)value;
+    } else if (k == "prefetch") {
+        c->prefetch = value != 0;
     } else if (k == "rotate") {
         c->rotate = value != 0;
     } else if (k == "stream_chunk_cols") {

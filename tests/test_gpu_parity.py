@@ -139,6 +139,23 @@ def test_cfg5_subset(ctx):
     check(ctx, p, lnl, joint)
 
 
+@pytest.mark.parametrize("opts", [dict(tile_m=4), dict(warps=8), dict(warps=15), dict(warps=8, rotate=0), dict(holes=0), dict(holes=1),
+                                  dict(rotate=0), dict(holes=0, rotate=0), dict(prefetch=1), dict(prefetch=1, rotate=0)])
+def test_kernel_variants_agree(ctx, opts):
+    """Every tuning variant of the pruning kernel (sr_set_option) gives oracle-exact results."""
+    p = synthetic(3, 512)
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
+    setup(ctx, p)
+    try:
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        r = ctx.run()
+        assert rel_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
+    finally:
+        for k, v in dict(tile_m=2, warps=11, holes=2, rotate=1, prefetch=0).items():
+            ctx.set_option(k, v)
+
+
 def test_ragged_offsets_and_chunks(ctx, example_problem):
     p = example_problem
     lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
