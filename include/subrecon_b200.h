@@ -59,6 +59,7 @@ typedef struct {
     double  ms_prune;   int64_t n_prune;        /* K2: post-order pruning (dominant)  */
     double  ms_root;    int64_t n_root;         /* K3: root-branch joint / marginal   */
     int64_t columns_pruned;                     /* columns processed by K2 launches   */
+    int64_t columns_in, columns_unique;         /* "compress_patterns": columns seen / distinct patterns computed */
 } sr_profile;
 
 /* Replaces: `Executors.newFixedThreadPool(nThreads)` (SubRecon.java:109) — the worker pool becomes a GPU. */
@@ -108,7 +109,8 @@ void sr_host_free(void *p);
 
 /* Tuning / introspection. Options: "tile_m" (MMA column tiles per warp: 2 or 4), "warps" (consumer warps per
  * CTA: 8, 11 or 15), "holes" (0..2 pauses inside a warp's MMA burst), "rotate" (0/1 burst hand-off between the warps of
- * an SM sub-partition), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage), "profile"
+ * an SM sub-partition), "compress_patterns" (0/1: compute each distinct column pattern of a batch once and copy the
+ * result to its duplicates; off by default), "prefetch" (experimental), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage), "profile"
  * (0/1: record per-kernel events), "rescale_every" (edges between power-of-two rescalings). */
 int sr_set_option(sr_ctx *ctx, const char *name, int64_t value);
 int sr_get_profile(sr_ctx *ctx, sr_profile *out);     /* synchronises the context's streams */

@@ -167,6 +167,71 @@ __global__ void __launch_bounds__(256) sanitize_kernel(uint4* __restrict__ v, si
     }
 }
 
+// ------------------------------------------------------------------------------------------- column patterns
+// Identical alignment columns have identical results, so a batch can be reduced to its distinct column patterns
+// (the reference recomputes every column, SubRecon.java:112-116). A pattern is identified by a 128-bit
+// hash of its state codes; equal hashes are treated as equal columns.
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {          // murmur3 finaliser
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+__global__ void __launch_bounds__(256) hash_columns_kernel(const uint8_t* __restrict__ states, int64_t pitch, int n_taxa,
+                                                           int64_t n, uint64_t* __restrict__ h1, uint64_t* __restrict__ h2,
+                                                           uint32_t* __restrict__ idx) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    uint64_t a = 0x9e3779b97f4a7c15ULL, b = 0xc2b2ae3d27d4eb4fULL;
+    for (int t = 0; t < n_taxa; ++t) {                           // adjacent threads read adjacent bytes of one row
+        const uint64_t v = states[(int64_t)t * pitch + c];
+        a = (a ^ v) * 0x100000001b3ULL;
+        b = mix64(b + v + 0x632be59bd9b4e019ULL * (uint64_t)(t + 1));
+    }
+    h1[c] = mix64(a);
+    h2[c] = b;
+    idx[c] = (uint32_t)c;
+}
+// after sorting (h1, idx): flag the first column of every run of equal (h1, h2)
+__global__ void __launch_bounds__(256) pattern_heads_kernel(const uint64_t* __restrict__ h1s, const uint32_t* __restrict__ idxs,
+                                                            const uint64_t* __restrict__ h2, int64_t n, int32_t* __restrict__ head) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || h1s[i] != h1s[i - 1] || h2[idxs[i]] != h2[idxs[i - 1]]) ? 1 : 0;
+}
+// uid = inclusive scan of head: pattern id (1-based) of the i-th sorted column
+__global__ void __launch_bounds__(256) pattern_map_kernel(const uint32_t* __restrict__ idxs, const int32_t* __restrict__ head,
+                                                          const int32_t* __restrict__ uid, int64_t n, uint32_t* __restrict__ rep,
+                                                          uint32_t* __restrict__ map) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t u = (uint32_t)uid[i] - 1;
+    map[idxs[i]] = u;
+    if (head[i]) rep[u] = idxs[i];
+}
+__global__ void __launch_bounds__(256) gather_patterns_kernel(const uint8_t* __restrict__ states, int64_t pitch, int n_taxa,
+                                                              const uint32_t* __restrict__ rep, int64_t n_uniq,
+                                                              uint8_t* __restrict__ out, int64_t out_pitch) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (u < out_pitch && t < n_taxa) out[(int64_t)t * out_pitch + u] = (u < n_uniq) ? states[(int64_t)t * pitch + rep[u]] : (uint8_t)NS;
+}
+// results of the distinct patterns back to every original column: one warp per column
+__global__ void __launch_bounds__(256) scatter_patterns_kernel(const uint32_t* __restrict__ map, int64_t n, int64_t out0,
+                                                               const double* __restrict__ u_lnl, const double* __restrict__ u_joint,
+                                                               const uint4* __restrict__ u_compact, double* __restrict__ lnl,
+                                                               double* __restrict__ joint, uint4* __restrict__ compact) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n; c += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const uint32_t u = map[c];
+        if (lnl && lane == 0) lnl[out0 + c] = u_lnl[u];
+        if (joint) {
+            const double2* src = reinterpret_cast<const double2*>(u_joint + (size_t)u * 400);
+            double2* dst = reinterpret_cast<double2*>(joint + (size_t)(out0 + c) * 400);
+            for (int e = lane; e < 200; e += 32) dst[e] = src[e];
+        }
+        if (compact && lane < 7) compact[(size_t)(out0 + c) * 7 + lane] = u_compact[(size_t)u * 7 + lane];   // 112 B = 7 x 16 B
+    }
+}
+
 // ------------------------------------------------------------------------------------------- K2
 // A pruning STEP (one ring stage, one loop iteration of a consumer warp) applies up to four edges:
 //     A  = / *=  T_pre0[state]          (n_pre >= 1; "=" when the step starts a new partial)

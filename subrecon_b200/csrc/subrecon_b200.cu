@@ -10,6 +10,7 @@
 
 #include "../../include/subrecon_b200.h"
 #include "kernels.cuh"
+#include <cub/cub.cuh>
 
 using namespace srk;
 
@@ -71,6 +72,7 @@ struct sr_ctx {
     // options
     int tile_m = 2;
     int holes = 2;                      // pauses inside a warp's MMA burst (0..2), see kernels.cuh
+    int compress = 0;                   // reduce every batch to its distinct column patterns first
     int prefetch = 0;                   // fetch the next step's first operands inside the current MMA burst
     int rotate = 1;                     // named-barrier burst rotation among the warps of an SM sub-partition
     int warps = 11;                     // consumer warps per CTA (tile_m == 2 only: 8, 11 or 15)
@@ -81,6 +83,8 @@ struct sr_ctx {
 
     // device state
     DevBuf d_model, d_rates, d_steps, d_stepoff, d_slotkind, d_slotoff, d_slotblen, d_pstream, d_proot, d_states, d_rootpart, d_rootexp, d_spill;
+    DevBuf d_pat_keys[2], d_pat_idx[2], d_pat_h2, d_pat_head, d_pat_uid, d_pat_rep, d_pat_map, d_pat_tmp, d_pat_states, d_pat_lnl, d_pat_joint, d_pat_compact;
+    int64_t last_unique = 0, last_total = 0;
     DevBuf d_chunk_states[2], d_chunk_lnl[2], d_chunk_joint[2], d_chunk_compact[2], d_peak;
     int32_t aln_taxa = 0;
     int64_t aln_sites = 0, aln_pitch = 0;
@@ -365,8 +369,8 @@ int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
 }
 
 // Columns [col_begin, col_begin+n) of a device block of states -> outputs (device pointers) at out0.
-int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch, int64_t col_begin, int64_t n,
-              double* d_lnl, double* d_joint, void* d_compact, double threshold, int64_t out0) {
+int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch, int64_t col_begin, int64_t n,
+                    double* d_lnl, double* d_joint, void* d_compact, double threshold, int64_t out0) {
     if (n <= 0) return SR_OK;
     int rc = ensure_pstream(c, s);
     if (rc) return rc;
@@ -426,6 +430,62 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
     return SR_OK;
 }
 
+
+// Optional front end: hash the columns, keep one representative per distinct pattern, run the path on those and copy
+// the results back to every column (bit-identical to the plain path: a column's result does not depend on its position).
+int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch, int n_taxa, int64_t col_begin, int64_t n,
+              double* d_lnl, double* d_joint, void* d_compact, double threshold, int64_t out0) {
+    if (!c->compress || n < 2) return run_block_plain(c, s, d_states, pitch, col_begin, n, d_lnl, d_joint, d_compact, threshold, out0);
+    if (n > (int64_t)1 << 31) return fail(c, SR_ERR_ARG, "too many columns in one launch; lower chunk_cols");
+    const uint8_t* base = d_states + col_begin;
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(c, c->d_pat_keys[i].reserve(sizeof(uint64_t) * n));
+        CUDA_TRY(c, c->d_pat_idx[i].reserve(sizeof(uint32_t) * n));
+    }
+    CUDA_TRY(c, c->d_pat_h2.reserve(sizeof(uint64_t) * n));
+    CUDA_TRY(c, c->d_pat_head.reserve(sizeof(int32_t) * n));
+    CUDA_TRY(c, c->d_pat_uid.reserve(sizeof(int32_t) * n));
+    CUDA_TRY(c, c->d_pat_rep.reserve(sizeof(uint32_t) * n));
+    CUDA_TRY(c, c->d_pat_map.reserve(sizeof(uint32_t) * n));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    hash_columns_kernel<<<nb, 256, 0, s>>>(base, pitch, n_taxa, n, c->d_pat_keys[0].as<uint64_t>(), c->d_pat_h2.as<uint64_t>(),
+                                           c->d_pat_idx[0].as<uint32_t>());
+    size_t tmp_sort = 0, tmp_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, c->d_pat_keys[0].as<uint64_t>(), c->d_pat_keys[1].as<uint64_t>(),
+                                    c->d_pat_idx[0].as<uint32_t>(), c->d_pat_idx[1].as<uint32_t>(), (int)n, 0, 64, s);
+    cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, c->d_pat_head.as<int32_t>(), c->d_pat_uid.as<int32_t>(), (int)n, s);
+    CUDA_TRY(c, c->d_pat_tmp.reserve(std::max(tmp_sort, tmp_scan)));
+    size_t tmp_bytes = c->d_pat_tmp.cap;
+    CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->d_pat_tmp.p, tmp_bytes, c->d_pat_keys[0].as<uint64_t>(), c->d_pat_keys[1].as<uint64_t>(),
+                                                c->d_pat_idx[0].as<uint32_t>(), c->d_pat_idx[1].as<uint32_t>(), (int)n, 0, 64, s));
+    pattern_heads_kernel<<<nb, 256, 0, s>>>(c->d_pat_keys[1].as<uint64_t>(), c->d_pat_idx[1].as<uint32_t>(), c->d_pat_h2.as<uint64_t>(), n,
+                                            c->d_pat_head.as<int32_t>());
+    tmp_bytes = c->d_pat_tmp.cap;
+    CUDA_TRY(c, cub::DeviceScan::InclusiveSum(c->d_pat_tmp.p, tmp_bytes, c->d_pat_head.as<int32_t>(), c->d_pat_uid.as<int32_t>(), (int)n, s));
+    pattern_map_kernel<<<nb, 256, 0, s>>>(c->d_pat_idx[1].as<uint32_t>(), c->d_pat_head.as<int32_t>(), c->d_pat_uid.as<int32_t>(), n,
+                                          c->d_pat_rep.as<uint32_t>(), c->d_pat_map.as<uint32_t>());
+    int32_t n_uniq = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&n_uniq, c->d_pat_uid.as<int32_t>() + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));               // the launch geometry below depends on the pattern count
+    c->last_unique += n_uniq;
+    c->last_total += n;
+    const int64_t up = (((int64_t)n_uniq + 255) / 256) * 256 + 256;
+    CUDA_TRY(c, c->d_pat_states.reserve((size_t)up * n_taxa + 512));
+    gather_patterns_kernel<<<dim3((unsigned)((up + 255) / 256), n_taxa), 256, 0, s>>>(base, pitch, n_taxa, c->d_pat_rep.as<uint32_t>(), n_uniq,
+                                                                                   c->d_pat_states.as<uint8_t>(), up);
+    CUDA_TRY(c, c->d_pat_lnl.reserve(sizeof(double) * n_uniq));
+    if (d_joint) CUDA_TRY(c, c->d_pat_joint.reserve(sizeof(double) * 400 * (size_t)n_uniq));
+    if (d_compact) CUDA_TRY(c, c->d_pat_compact.reserve(sizeof(sr_compact) * (size_t)n_uniq));
+    int rc = run_block_plain(c, s, c->d_pat_states.as<uint8_t>(), up, 0, n_uniq, c->d_pat_lnl.as<double>(),
+                             d_joint ? c->d_pat_joint.as<double>() : nullptr, d_compact ? c->d_pat_compact.p : nullptr, threshold, 0);
+    if (rc) return rc;
+    scatter_patterns_kernel<<<c->n_sm * 16, 256, 0, s>>>(c->d_pat_map.as<uint32_t>(), n, out0, c->d_pat_lnl.as<double>(),
+                                                         d_joint ? c->d_pat_joint.as<double>() : nullptr,
+                                                         d_compact ? c->d_pat_compact.as<uint4>() : nullptr, d_lnl, d_joint,
+                                                         reinterpret_cast<uint4*>(d_compact));
+    CUDA_TRY(c, cudaGetLastError());
+    return SR_OK;
+}
 
 int check_run_args(sr_ctx* c, int64_t site0, int64_t n, int64_t n_sites, const void* lnl) {
     if (!c) return SR_ERR_ARG;
@@ -576,7 +636,7 @@ int sr_run_device(sr_ctx* c, int64_t site0, int64_t n, double* d_lnl, double* d_
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     for (int64_t done = 0; done < n;) {
         const int64_t m = std::min(n - done, c->chunk_cols);
-        rc = run_block(c, s, c->d_states.as<uint8_t>(), c->aln_pitch, site0 + done, m, d_lnl, d_joint, d_compact, threshold, done);
+        rc = run_block(c, s, c->d_states.as<uint8_t>(), c->aln_pitch, c->aln_taxa, site0 + done, m, d_lnl, d_joint, d_compact, threshold, done);
         if (rc) return rc;
         done += m;
     }
@@ -608,7 +668,7 @@ int sr_run(sr_ctx* c, int64_t site0, int64_t n, double* lnl, double* joint, sr_c
         if (joint && c->d_chunk_joint[b].reserve(sizeof(double) * 400 * m) != cudaSuccess) { rc = fail(c, SR_ERR_OOM, "device OOM (joint chunk)"); break; }
         if (compact && c->d_chunk_compact[b].reserve(sizeof(sr_compact) * m) != cudaSuccess) { rc = fail(c, SR_ERR_OOM, "device OOM (compact chunk)"); break; }
         if (ci >= 2) cudaStreamWaitEvent(c->stream, free_ev[b], 0);      // buffer b drained?
-        rc = run_block(c, c->stream, c->d_states.as<uint8_t>(), c->aln_pitch, site0 + done, m, c->d_chunk_lnl[b].as<double>(),
+        rc = run_block(c, c->stream, c->d_states.as<uint8_t>(), c->aln_pitch, c->aln_taxa, site0 + done, m, c->d_chunk_lnl[b].as<double>(),
                        joint ? c->d_chunk_joint[b].as<double>() : nullptr, compact ? c->d_chunk_compact[b].p : nullptr, threshold, 0);
         if (rc) break;
         cudaEventRecord(done_ev[b], c->stream);
@@ -668,7 +728,7 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
         cudaEventRecord(up_ev[b], c->s_h2d);
         cudaStreamWaitEvent(c->stream, up_ev[b], 0);
         if (ci >= 2) cudaStreamWaitEvent(c->stream, free_ev[b], 0);     // output buffers b drained
-        rc = run_block(c, c->stream, c->d_chunk_states[b].as<uint8_t>(), cpitch, 0, m, c->d_chunk_lnl[b].as<double>(),
+        rc = run_block(c, c->stream, c->d_chunk_states[b].as<uint8_t>(), cpitch, n_taxa, 0, m, c->d_chunk_lnl[b].as<double>(),
                        joint ? c->d_chunk_joint[b].as<double>() : nullptr, compact ? c->d_chunk_compact[b].p : nullptr, threshold, 0);
         if (rc) break;
         cudaEventRecord(done_ev[b], c->stream);
@@ -716,6 +776,9 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     } else if (k == "holes") {
         if (value < 0 || value > 2) return fail(c, SR_ERR_ARG, "holes must be 0, 1 or 2");
         c->holes = (int)value;
+    } else if (k == "compress_patterns") {
+        c->compress = value != 0;
+        c->last_unique = c->last_total = 0;
     } else if (k == "prefetch") {
         c->prefetch = value != 0;
     } else if (k == "rotate") {
@@ -751,6 +814,8 @@ int sr_get_profile(sr_ctx* c, sr_profile* out) {
         cudaEventDestroy(e.a); cudaEventDestroy(e.b);
     }
     c->events.clear();
+    c->prof.columns_in = c->last_total;
+    c->prof.columns_unique = c->last_unique;
     *out = c->prof;
     return SR_OK;
 }
@@ -760,6 +825,7 @@ int sr_profile_reset(sr_ctx* c) {
     sr_profile tmp;
     int rc = sr_get_profile(c, &tmp);
     c->prof = sr_profile{};
+    c->last_unique = c->last_total = 0;
     return rc;
 }
 

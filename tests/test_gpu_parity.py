@@ -180,6 +180,36 @@ def test_ragged_offsets_and_chunks(ctx, example_problem):
     assert rel_err(one["lnl"], np.tile(lnl, 9)) < TOL
 
 
+def test_column_pattern_compression(ctx, example_problem):
+    """compute each distinct column once. Results must be bit-identical to the plain path."""
+    p = example_problem
+    setup(ctx, p)
+    plain = ctx.run(want_joint=True, want_compact=True, threshold=0.3)
+    try:
+        ctx.set_option("compress_patterns", 1)
+        ctx.profile(reset=True)
+        comp = ctx.run(want_joint=True, want_compact=True, threshold=0.3)
+        prof = ctx.profile(reset=True)
+        assert prof["columns_in"] == 130 and prof["columns_unique"] == 51          # SURVEY §8d: 51 distinct columns
+        for k in ("lnl", "joint"):
+            assert np.array_equal(plain[k], comp[k])
+        assert plain["compact"].tobytes() == comp["compact"].tobytes()
+        # ragged window + a big batch of repeats + the streamed pipeline
+        w = ctx.run(site0=7, n=101)
+        assert np.array_equal(w["lnl"], plain["lnl"][7:108]) and np.array_equal(w["joint"], plain["joint"][7:108])
+        big = np.tile(p.states, (1, 300))
+        ctx.set_alignment(big)
+        ctx.profile(reset=True)
+        r = ctx.run(want_joint=False)
+        prof = ctx.profile(reset=True)
+        assert prof["columns_unique"] == 51 and prof["columns_in"] == 39000
+        assert np.array_equal(r["lnl"], np.tile(plain["lnl"], 300))
+        st = ctx.run_streamed(big)
+        assert np.array_equal(st["lnl"], r["lnl"]) and np.array_equal(st["joint"][:130], plain["joint"])
+    finally:
+        ctx.set_option("compress_patterns", 0)
+
+
 def test_pinned_buffers(ctx, example_problem):
     p = example_problem
     setup(ctx, p)
