@@ -108,7 +108,7 @@ void *sr_host_alloc(size_t bytes);
 void sr_host_free(void *p);
 
 /* Tuning / introspection. Options: "tile_m" (MMA column tiles per warp: 2 or 4), "warps" (consumer warps per
- * CTA: 8, 11 or 15), "holes" (0..2 pauses inside a warp's MMA burst), "rotate" (0/1 burst hand-off between the warps of
+ * CTA: 8, 11, 15, or 12 = experimental variant without a producer warp), "holes" (0..2 pauses inside a warp's MMA burst), "rotate" (0/1 burst hand-off between the warps of
  * an SM sub-partition), "compress_patterns" (0/1: compute each distinct column pattern of a batch once and copy the
  * result to its duplicates; off by default), "prefetch" (experimental), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage), "profile"
  * (0/1: record per-kernel events), "rescale_every" (edges between power-of-two rescalings). */

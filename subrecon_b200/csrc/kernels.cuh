@@ -290,8 +290,12 @@ __host__ __device__ constexpr int prune_bar_bytes(int nstage) { return ((2 * nst
 __device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false, bool PREF = false>
-__global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) {
+// INL: no dedicated producer warp. A ring stage is released by counting the consumer warps on a shared-memory counter;
+// the warp that releases it LAST immediately issues the TMA copies of the step NSTAGE positions ahead into it. Nobody ever
+// blocks on an "empty" barrier, and all W_ warps of the CTA are consumers, so each SM sub-partition gets the same number
+// of MMA warps (with a producer warp, its sub-partition runs one consumer short and its tensor pipe idles a third of the time).
+template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false>
+__global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(PruneParams p) {
     using Cfg = PruneCfg<M, W_>;
     constexpr int W = Cfg::W;
     constexpr int S = Cfg::S;
@@ -305,7 +309,10 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&full[s], 1);
+            if (INL) empty[s] = 0; else mbar_init(&empty[s], W);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -313,28 +320,29 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
     const int n_items = p.n_tiles * p.K;
     uint32_t it = 0;                                  // ring position, runs on across work items
 
-    if (warp == W) {
+    // issue the TMA copies of one step (global ring position itp; work item `item_p`, step `step_p`) — one thread
+    auto issue_step = [&](uint32_t itp, int item_p, const int4 d, const int off_d, bool wait_empty) {
+        const int kp = item_p / p.n_tiles, tilep = item_p - kp * p.n_tiles;
+        const double* ps = p.pstream + (size_t)kp * p.rate_stride;
+        const uint8_t* st = p.states + p.col0 + (int64_t)tilep * S;
+        const int stage = itp % NSTAGE;
+        const uint32_t ph = (itp / NSTAGE) & 1;
+        const int n_leaf = ((d.x >> ST_NPRE_SHIFT) & 3) + ((d.x & ST_NPOST) ? 1 : 0);
+        const uint32_t pbytes = ((d.x & ST_MV_MASK) ? FRAG_BYTES : 0) + n_leaf * TABLE_BYTES;
+        if (wait_empty) mbar_wait(&empty[stage], ph ^ 1);
+        unsigned char* dst = stages + stage * STAGE_BYTES;
+        mbar_expect_tx(&full[stage], pbytes + n_leaf * S);
+        bulk_g2s(dst, ps + off_d, pbytes, &full[stage]);
+        if (n_leaf > 0) bulk_g2s(dst + Cfg::STATES_OFF, st + (int64_t)d.y * p.pitch, S, &full[stage]);
+        if (n_leaf > 1) bulk_g2s(dst + Cfg::STATES_OFF + S, st + (int64_t)d.z * p.pitch, S, &full[stage]);
+        if (n_leaf > 2) bulk_g2s(dst + Cfg::STATES_OFF + 2 * S, st + (int64_t)d.w * p.pitch, S, &full[stage]);
+    };
+
+    if (!INL && warp == W) {
         // ===== producer: one lane streams every step's matrices (and tip states) into the ring =====
         if (lane == 0) {
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int k = item / p.n_tiles, tile = item - k * p.n_tiles;
-                const double* ps = p.pstream + (size_t)k * p.rate_stride;
-                const uint8_t* st = p.states + p.col0 + (int64_t)tile * S;
-                for (int step = 0; step < p.n_steps; ++step, ++it) {
-                    const int stage = it % NSTAGE;
-                    const uint32_t ph = (it / NSTAGE) & 1;
-                    const int4 d = __ldg(p.steps + step);
-                    const int n_leaf = ((d.x >> ST_NPRE_SHIFT) & 3) + ((d.x & ST_NPOST) ? 1 : 0);
-                    const uint32_t pbytes = ((d.x & ST_MV_MASK) ? FRAG_BYTES : 0) + n_leaf * TABLE_BYTES;
-                    mbar_wait(&empty[stage], ph ^ 1);
-                    unsigned char* dst = stages + stage * STAGE_BYTES;
-                    mbar_expect_tx(&full[stage], pbytes + n_leaf * S);
-                    bulk_g2s(dst, ps + __ldg(p.step_off + step), pbytes, &full[stage]);
-                    if (n_leaf > 0) bulk_g2s(dst + Cfg::STATES_OFF, st + (int64_t)d.y * p.pitch, S, &full[stage]);
-                    if (n_leaf > 1) bulk_g2s(dst + Cfg::STATES_OFF + S, st + (int64_t)d.z * p.pitch, S, &full[stage]);
-                    if (n_leaf > 2) bulk_g2s(dst + Cfg::STATES_OFF + 2 * S, st + (int64_t)d.w * p.pitch, S, &full[stage]);
-                }
-            }
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+                for (int step = 0; step < p.n_steps; ++step, ++it) issue_step(it, item, __ldg(p.steps + step), __ldg(p.step_off + step), true);
         }
         return;
     }
@@ -351,7 +359,33 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
     const int bar_wait_id = sp4 * 4 + (rpos + n_rot - 1) % n_rot;         // armed by the previous warp in the rotation
     const int bar_pass_id = sp4 * 4 + rpos;
     bool first_burst = (rpos == 0);
-
+    // INL: look-ahead cursor = the (item, step) that sits NSTAGE ring positions ahead of this warp's current step
+    int la_item = blockIdx.x, la_step = 0;
+    uint32_t la_it = 0;
+    int4 la_d = make_int4(0, 0, 0, 0);                // descriptor of the look-ahead step, fetched a whole iteration early
+    int la_off = 0;
+    int* rel_cnt = reinterpret_cast<int*>(empty);     // the "empty" mbarrier slots double as plain release counters
+    if (INL) {
+        for (int d = 0; d < NSTAGE; ++d) {            // prologue: fill every stage once
+            if (la_item < n_items && warp == 0 && lane == 0) issue_step(la_it, la_item, __ldg(p.steps + la_step), __ldg(p.step_off + la_step), false);
+            ++la_it;
+            if (++la_step == p.n_steps) { la_step = 0; la_item += gridDim.x; }
+        }
+    }
+    // release of the stage used by ring position `it` (all of this warp's reads of it are complete)
+    auto release_stage = [&](int stage) {
+        if (!INL) {
+            if (lane == 0) mbar_arrive(&empty[stage]);
+        } else if (lane == 0) {
+            // relaxed is enough: every read of the stage by this warp has completed (its value was consumed by an issued
+            // instruction) before this point, and the refill below is ordered after the atomics of all other warps
+            const int old = atomicAdd(&rel_cnt[stage * 2], 1);
+            if (old == W - 1) {                       // last consumer out: refill the stage for ring position it + NSTAGE
+                rel_cnt[stage * 2] = 0;
+                if (la_item < n_items) issue_step(la_it, la_item, la_d, la_off, false);
+            }
+        }
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int k = item / p.n_tiles, tile = item - k * p.n_tiles;
         double A[M][5];
@@ -387,6 +421,7 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
             const int w = w_next;
             const bool has_next = step + 1 < p.n_steps;
             if (has_next) w_next = __ldg(&p.steps[step + 1].x);
+            if (INL && la_item < n_items) { la_d = __ldg(p.steps + la_step); la_off = __ldg(p.step_off + la_step); }
             const int mv = w & ST_MV_MASK, n_pre = (w >> ST_NPRE_SHIFT) & 3;
             const unsigned char* stg = stages + stage * STAGE_BYTES;
             const double2* frag = reinterpret_cast<const double2*>(stg) + lane;
@@ -542,7 +577,7 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
                 }
                 if (!LAZY) {      // every read of the stage was issued before (or inside) the burst and its value has been
                     __syncwarp(); // consumed by an issued DMMA/DMUL or sits in a register: nothing left for the TMA to race
-                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    release_stage(stage);
                 }
 #pragma unroll
                 for (int j = 0; j < M; ++j)
@@ -570,7 +605,13 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
                     stage_release(&empty[stage], lane);
                 }
             } else {
-                stage_release(&empty[stage], lane);
+                if (INL) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    release_stage(stage);
+                } else {
+                    stage_release(&empty[stage], lane);
+                }
                 if (PREF && has_next) {          // no burst to hide behind: fetch the next step's first operands here
                     const double2* fragn = reinterpret_cast<const double2*>(stgn) + lane;
                     const unsigned char* stbn = stgn + st_lane_off;
@@ -583,6 +624,10 @@ __global__ void __launch_bounds__((W_ + 1) * 32, 1) prune_kernel(PruneParams p) 
             if (PREF && has_next) {
 #pragma unroll
                 for (int j = 0; j < M; ++j) { s0[j] = sn0[j]; s1[j] = sn1[j]; s2[j] = sn2[j]; }
+            }
+            if (INL) {
+                ++la_it;
+                if (++la_step == p.n_steps) { la_step = 0; la_item += gridDim.x; }
             }
             if (w & STF_ANY) {
                 if (w & STF_RESCALE) {

@@ -344,7 +344,7 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     return SR_OK;
 }
 
-template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false, bool PREF = false>
+template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false>
 int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     using Cfg = PruneCfg<M, W>;
     const int fixed = NSTAGE * Cfg::STAGE_BYTES + prune_bar_bytes(NSTAGE);
@@ -359,10 +359,10 @@ int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     p.spill_levels = spill_levels;
     p.spill = c->d_spill.as<double>();
     const int smem = fixed + levels * Cfg::LEVEL_BYTES;
-    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT, PREF>;
+    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT, PREF, INL>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prof_begin(c, s, 1, cols);
-    kern<<<grid, Cfg::THREADS, smem, s>>>(p);
+    kern<<<grid, (W + (INL ? 0 : 1)) * 32, smem, s>>>(p);
     prof_end(c, s);
     CUDA_TRY(c, cudaGetLastError());
     return SR_OK;
@@ -399,6 +399,7 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     // kernel variants: tile_m (column tiles per warp), consumer warps, holes in the MMA burst, burst rotation
     const int hl = c->holes, rot = c->rotate;
     if (c->tile_m == 4) rc = launch_prune<4, 4, 8>(c, s, p, n);
+    else if (c->warps == 12) rc = rot ? launch_prune<2, 4, 12, 2, true, false, true>(c, s, p, n) : launch_prune<2, 4, 12, 2, false, false, true>(c, s, p, n);
     else if (c->warps == 8) rc = rot ? launch_prune<2, 4, 8, 2, true>(c, s, p, n) : launch_prune<2, 4, 8, 0, false>(c, s, p, n);
     else if (c->warps == 15) rc = rot ? launch_prune<2, 4, 15, 2, true>(c, s, p, n) : launch_prune<2, 4, 15, 0, false>(c, s, p, n);
     else if (c->prefetch && rot) rc = launch_prune<2, 4, 11, 2, true, true>(c, s, p, n);
@@ -700,8 +701,19 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
     rc = ensure_pstream(c, c->stream);
     if (rc) return rc;
     // three-stage pipeline over column chunks: H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h), two buffers each
-    const int64_t chunk = std::max<int64_t>(256, (std::min<int64_t>(std::min(c->chunk_cols, c->stream_chunk_cols), std::max<int64_t>(n, 1)) + 255) / 256 * 256);
-    const int64_t cpitch = chunk + 256;
+    // Pipeline chunk: about stream_chunk_cols columns, rounded to a whole number of persistent-kernel waves
+    // (tiles x K work items must be a multiple of the SM count, or the last wave of every chunk runs part empty).
+    int64_t chunk;
+    {
+        const int64_t S = (int64_t)c->warps * c->tile_m * 8;
+        int64_t g = c->n_sm, b = std::max(1, c->K);
+        while (b) { const int64_t t = g % b; g = b; b = t; }
+        const int64_t unit = (c->n_sm / g) * S;                       // columns per whole wave set
+        const int64_t target = std::min<int64_t>(std::min(c->chunk_cols, c->stream_chunk_cols), std::max<int64_t>(n, 1));
+        chunk = (target >= unit) ? (target / unit) * unit : (target + 255) / 256 * 256;
+        chunk = std::max<int64_t>(256, (chunk + 15) / 16 * 16);
+    }
+    const int64_t cpitch = (chunk + 255) / 256 * 256 + 256;
     cudaEvent_t up_ev[2], done_ev[2], free_ev[2], sfree_ev[2];
     for (int i = 0; i < 2; ++i) {
         CUDA_TRY(c, cudaEventCreateWithFlags(&up_ev[i], cudaEventDisableTiming));
@@ -767,7 +779,7 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
         c->warps = (value == 4) ? 8 : 11;
     } else if (k == "warps") {
         // register files are allocated in 4-warp granules: with the producer warp, 11 and 15 consumers are "free"
-        if (value != 8 && value != 11 && value != 15) return fail(c, SR_ERR_ARG, "warps must be 8, 11 or 15");
+        if (value != 8 && value != 11 && value != 12 && value != 15) return fail(c, SR_ERR_ARG, "warps must be 8, 11, 12 or 15");
         if (c->tile_m == 4 && value != 8) return fail(c, SR_ERR_ARG, "tile_m 4 supports 8 warps only");
         c->warps = (int)value;
     } else if (k == "chunk_cols") {

@@ -140,7 +140,7 @@ def test_cfg5_subset(ctx):
 
 
 @pytest.mark.parametrize("opts", [dict(tile_m=4), dict(warps=8), dict(warps=15), dict(warps=8, rotate=0), dict(holes=0), dict(holes=1),
-                                  dict(rotate=0), dict(holes=0, rotate=0), dict(prefetch=1), dict(prefetch=1, rotate=0)])
+                                  dict(rotate=0), dict(holes=0, rotate=0), dict(prefetch=1), dict(prefetch=1, rotate=0), dict(warps=12), dict(warps=12, rotate=0)])
 def test_kernel_variants_agree(ctx, opts):
     """Every tuning variant of the pruning kernel (sr_set_option) gives oracle-exact results."""
     p = synthetic(3, 512)
