@@ -132,6 +132,48 @@ def test_cfg4_deep_caterpillar_rescaling(ctx):
     ctx.set_option("rescale_every", 8)
 
 
+def test_cfg4_full_size_properties(ctx):
+    """BASELINE config #4 at full size (5,000-taxon caterpillar x 200k sites, K=8): 1,024 simulated columns repeated;
+    every copy bit-identical, the first block equal to the oracle, posteriors sum to 1."""
+    p = synthetic(4, 1024)
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
+    setup(ctx, p)
+    big = np.tile(p.states, (1, 196))[:, :200_000]
+    ctx.set_alignment(big)
+    r = ctx.run(want_joint=False, want_compact=True, threshold=0.5)
+    assert r["lnl"].shape == (200_000,)
+    assert np.array_equal(r["lnl"], np.tile(r["lnl"][:1024], 196)[:200_000])
+    assert rel_err(r["lnl"][:1024], lnl) < TOL
+    assert rel_err(r["compact"]["max_prob"][:1024], joint.max(axis=(1, 2))) < TOL
+    tail = ctx.run(site0=199_000, n=1000)
+    assert np.max(np.abs(tail["joint"].sum(axis=(1, 2)) - 1.0)) < 1e-12
+    assert np.array_equal(tail["lnl"], r["lnl"][199_000:])
+
+
+def test_cfg5_full_size_properties(ctx):
+    """BASELINE config #5 at full size (2,000 taxa x 8M sites, Dayhoff): streamed from host memory in column chunks
+    with the compact result; 2,048 simulated columns repeated, every copy bit-identical, first block equal to the oracle."""
+    import psutil
+    if psutil.virtual_memory().available < 40 * 2**30:
+        pytest.skip("needs ~17 GB of host memory for the 2,000 x 8M state matrix")
+    p = synthetic(5, 2048)
+    lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
+    setup(ctx, p)
+    L = 8_000_000
+    big = np.empty((p.states.shape[0], L), dtype=np.uint8)
+    for c0 in range(0, L, 2048):
+        w = min(2048, L - c0)
+        big[:, c0:c0 + w] = p.states[:, :w]
+    r = ctx.run_streamed(big, want_joint=False, want_compact=True, threshold=0.5)
+    del big
+    assert r["lnl"].shape == (L,)
+    ref = np.tile(r["lnl"][:2048], L // 2048 + 1)[:L]
+    assert np.array_equal(r["lnl"], ref)
+    assert rel_err(r["lnl"][:2048], lnl) < TOL
+    assert np.array_equal(r["compact"]["lnl"], r["lnl"])
+    assert rel_err(r["compact"]["max_ii_prob"][:2048], np.diagonal(joint, axis1=1, axis2=2).max(axis=1)) < TOL
+
+
 def test_cfg5_subset(ctx):
     p = synthetic(5, 2048)
     lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
