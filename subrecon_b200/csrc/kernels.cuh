@@ -399,8 +399,12 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
         int sp = 0;
         int w_next = __ldg(&p.steps[0].x);
         bool next_ready = false;           // result of an early, non-blocking probe of a later stage's full barrier
-        static_assert(!PREF || HOLES == 2, "cross-step prefetch rides on the first hole of the burst");
-        constexpr int FIRST = (HOLES == 0) ? 8 : (HOLES == 1 ? 5 : 3);      // fragment pairs fetched before the burst
+        // HOLES encodes before which k-steps the burst pauses: 0 none, 1 -> {3}, 2 -> {2,4}, two digits ab -> {a,b}
+        constexpr int H1 = (HOLES == 0) ? 9 : (HOLES == 1 ? 3 : (HOLES == 2 ? 2 : HOLES / 10));
+        constexpr int H2 = (HOLES == 0 || HOLES == 1) ? 9 : (HOLES == 2 ? 4 : HOLES % 10);
+        constexpr int PAIRS0 = (H1 >= 5) ? 8 : (3 * H1 + 1) / 2;          // pairs covering fragments [0, 3*H1)
+        constexpr int PAIRS1 = (H2 >= 5) ? 8 : (3 * H2 + 1) / 2;          // ... [0, 3*H2)
+        constexpr int FIRST = PAIRS0;                                      // fragment pairs fetched before the burst
         int s0[M], s1[M], s2[M];
         double Bf[16];
         if (PREF) {
@@ -522,14 +526,13 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                 }
 #pragma unroll
                 for (int s = 0; s < 5; ++s) {
-                    // HOLES == 1: pairs 5..7 (fragments 10..15) before s = 3 (uses 9..11: fragment 9 came with pair 4)
-                    // HOLES == 2: pairs 3..5 before s = 2 (fragments 6..11), pairs 6..7 before s = 4 (12..14)
-                    if ((HOLES == 1 && s == 3) || (HOLES == 2 && (s == 2 || s == 4))) {
+                    // just-in-time fragment fetch: the pairs the next chunk needs are loaded only now, so the warp pauses
+                    if (s == H1 || s == H2) {
                         asm volatile("" ::: "memory");
-                        const int lo = (HOLES == 1) ? 5 : (s == 2 ? 3 : 6), hi = (HOLES == 2 && s == 2) ? 6 : 8;
+                        const int lo = (s == H1) ? PAIRS0 : PAIRS1, hi = (s == H1) ? PAIRS1 : 8;
 #pragma unroll
                         for (int i = lo; i < hi; ++i) { const double2 v = frag[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
-                        if (PREF && s == 2 && has_next) {
+                        if (PREF && s == H1 && has_next) {
                             // fragments 0..5 are dead (k-steps 0,1 issued): refill them, and the tip state codes, for step+1
                             const double2* fragn = reinterpret_cast<const double2*>(stgn) + lane;
                             const unsigned char* stbn = stgn + st_lane_off;

@@ -404,6 +404,11 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     else if (c->warps == 15) rc = rot ? launch_prune<2, 4, 15, 2, true>(c, s, p, n) : launch_prune<2, 4, 15, 0, false>(c, s, p, n);
     else if (c->prefetch && rot) rc = launch_prune<2, 4, 11, 2, true, true>(c, s, p, n);
     else if (c->prefetch) rc = launch_prune<2, 4, 11, 2, false, true>(c, s, p, n);
+    else if (rot && hl == 13) rc = launch_prune<2, 4, 11, 13, true>(c, s, p, n);
+    else if (rot && hl == 12) rc = launch_prune<2, 4, 11, 12, true>(c, s, p, n);
+    else if (rot && hl == 23) rc = launch_prune<2, 4, 11, 23, true>(c, s, p, n);
+    else if (rot && hl == 14) rc = launch_prune<2, 4, 11, 14, true>(c, s, p, n);
+    else if (rot && hl == 34) rc = launch_prune<2, 4, 11, 34, true>(c, s, p, n);
     else if (rot) rc = (hl == 0) ? launch_prune<2, 4, 11, 0, true>(c, s, p, n)
                      : (hl == 1) ? launch_prune<2, 4, 11, 1, true>(c, s, p, n) : launch_prune<2, 4, 11, 2, true>(c, s, p, n);
     else rc = (hl == 0) ? launch_prune<2, 4, 11, 0, false>(c, s, p, n)
@@ -786,7 +791,7 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
         if (value < 256) return fail(c, SR_ERR_ARG, "chunk_cols must be >= 256");
         c->chunk_cols = (value + 255) / 256 * 256;
     } else if (k == "holes") {
-        if (value < 0 || value > 2) return fail(c, SR_ERR_ARG, "holes must be 0, 1 or 2");
+        if (value < 0 || value > 44) return fail(c, SR_ERR_ARG, "holes must be 0, 1, 2 or a two-digit k-step pair");
         c->holes = (int)value;
     } else if (k == "compress_patterns") {
         c->compress = value != 0;
