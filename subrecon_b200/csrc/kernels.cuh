@@ -61,6 +61,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a hardware time slice when the phase is still open)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
@@ -290,10 +300,11 @@ __host__ __device__ constexpr int prune_bar_bytes(int nstage) { return ((2 * nst
 __device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-// INL: no dedicated producer warp. A ring stage is released by counting the consumer warps on a shared-memory counter;
-// the warp that releases it LAST immediately issues the TMA copies of the step NSTAGE positions ahead into it. Nobody ever
-// blocks on an "empty" barrier, and all W_ warps of the CTA are consumers, so each SM sub-partition gets the same number
-// of MMA warps (with a producer warp, its sub-partition runs one consumer short and its tensor pipe idles a third of the time).
+// INL: no dedicated producer warp. Ring position P is refilled by consumer warp (P mod W): once per iteration it probes
+// (non-blocking) the "empty" barrier of the stage its next position lives in and issues the TMA copies if every warp has
+// released it; it only blocks when it reaches a position it has not requested yet. All W_ warps of the CTA are consumers,
+// so each SM sub-partition gets the same number of MMA warps (with a producer warp, its sub-partition runs one consumer
+// short and its tensor pipe idles a third of the time).
 template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false>
 __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(PruneParams p) {
     using Cfg = PruneCfg<M, W_>;
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], 1);
-            if (INL) empty[s] = 0; else mbar_init(&empty[s], W);
+            mbar_init(&empty[s], W);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -359,32 +370,39 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
     const int bar_wait_id = sp4 * 4 + (rpos + n_rot - 1) % n_rot;         // armed by the previous warp in the rotation
     const int bar_pass_id = sp4 * 4 + rpos;
     bool first_burst = (rpos == 0);
-    // INL: look-ahead cursor = the (item, step) that sits NSTAGE ring positions ahead of this warp's current step
-    int la_item = blockIdx.x, la_step = 0;
-    uint32_t la_it = 0;
-    int4 la_d = make_int4(0, 0, 0, 0);                // descriptor of the look-ahead step, fetched a whole iteration early
-    int la_off = 0;
-    int* rel_cnt = reinterpret_cast<int*>(empty);     // the "empty" mbarrier slots double as plain release counters
+    // INL: this warp refills ring positions my_pos = warp, warp + W, warp + 2W, ... (cursor: work item / step / descriptor)
+    uint32_t my_pos = (uint32_t)warp;
+    int my_item = blockIdx.x, my_step = warp;
+    int4 my_d = make_int4(0, 0, 0, 0);
+    int my_off = 0;
+    auto my_normalise = [&]() {
+        while (my_item < n_items && my_step >= p.n_steps) { my_step -= p.n_steps; my_item += gridDim.x; }
+        if (my_item < n_items) { my_d = __ldg(p.steps + my_step); my_off = __ldg(p.step_off + my_step); }
+    };
+    // try (or, if `block`, wait) to refill my next position; returns after at most one refill
+    auto my_refill = [&](bool block) {
+        if (my_item >= n_items) return;
+        // Only once this warp itself is past position my_pos - NSTAGE: then the stage's "empty" barrier is at most one
+        // phase behind and the parity test below is unambiguous (a single in-order producer gets this for free).
+        if (my_pos >= it + NSTAGE) return;
+        const int stg_ = my_pos % NSTAGE;
+        const uint32_t par_ = ((my_pos / NSTAGE) & 1) ^ 1;
+        bool ok = mbar_test_wait(&empty[stg_], par_);
+        if (!ok && block) { mbar_wait(&empty[stg_], par_); ok = true; }
+        if (!ok) return;
+        if (lane == 0) issue_step(my_pos, my_item, my_d, my_off, false);
+        __syncwarp();
+        my_pos += W;
+        my_step += W;
+        my_normalise();
+    };
     if (INL) {
-        for (int d = 0; d < NSTAGE; ++d) {            // prologue: fill every stage once
-            if (la_item < n_items && warp == 0 && lane == 0) issue_step(la_it, la_item, __ldg(p.steps + la_step), __ldg(p.step_off + la_step), false);
-            ++la_it;
-            if (++la_step == p.n_steps) { la_step = 0; la_item += gridDim.x; }
-        }
+        my_normalise();
+        if (warp < NSTAGE) my_refill(true);           // the first NSTAGE positions find their stages empty
     }
     // release of the stage used by ring position `it` (all of this warp's reads of it are complete)
     auto release_stage = [&](int stage) {
-        if (!INL) {
-            if (lane == 0) mbar_arrive(&empty[stage]);
-        } else if (lane == 0) {
-            // relaxed is enough: every read of the stage by this warp has completed (its value was consumed by an issued
-            // instruction) before this point, and the refill below is ordered after the atomics of all other warps
-            const int old = atomicAdd(&rel_cnt[stage * 2], 1);
-            if (old == W - 1) {                       // last consumer out: refill the stage for ring position it + NSTAGE
-                rel_cnt[stage * 2] = 0;
-                if (la_item < n_items) issue_step(la_it, la_item, la_d, la_off, false);
-            }
-        }
+        if (lane == 0) mbar_arrive(&empty[stage]);
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int k = item / p.n_tiles, tile = item - k * p.n_tiles;
@@ -425,7 +443,7 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
             const int w = w_next;
             const bool has_next = step + 1 < p.n_steps;
             if (has_next) w_next = __ldg(&p.steps[step + 1].x);
-            if (INL && la_item < n_items) { la_d = __ldg(p.steps + la_step); la_off = __ldg(p.step_off + la_step); }
+            if (INL) my_refill(/*block=*/my_pos <= it);
             const int mv = w & ST_MV_MASK, n_pre = (w >> ST_NPRE_SHIFT) & 3;
             const unsigned char* stg = stages + stage * STAGE_BYTES;
             const double2* frag = reinterpret_cast<const double2*>(stg) + lane;
@@ -550,7 +568,7 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                 if (ROT && n_rot > 1) bar_arrive64(bar_pass_id);
                 {   // probe the next stage now: the ~60-cycle TRYWAIT latency hides behind this step's epilogue
                     const uint32_t itp = it + (PREF ? 2 : 1);
-                    next_ready = mbar_try_wait(&full[itp % NSTAGE], (itp / NSTAGE) & 1);
+                    next_ready = mbar_test_wait(&full[itp % NSTAGE], (itp / NSTAGE) & 1);
                 }
                 if (LAZY) {
                     if (w & ST_NPOST) {
@@ -627,10 +645,6 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
             if (PREF && has_next) {
 #pragma unroll
                 for (int j = 0; j < M; ++j) { s0[j] = sn0[j]; s1[j] = sn1[j]; s2[j] = sn2[j]; }
-            }
-            if (INL) {
-                ++la_it;
-                if (++la_step == p.n_steps) { la_step = 0; la_item += gridDim.x; }
             }
             if (w & STF_ANY) {
                 if (w & STF_RESCALE) {
