@@ -520,17 +520,29 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                 }
             }
             // ... products after all of them are in flight
-            if (n_pre >= 1) {
+            if (n_pre == 2 && (w & ST_PRE0_SET)) {                       // cherry: the common case, no selects
 #pragma unroll
                 for (int j = 0; j < M; ++j)
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) A[j][r] = (w & ST_PRE0_SET) ? tp0[j][r] : A[j][r] * tp0[j][r];
-            }
-            if (n_pre == 2) {
+                    for (int r = 0; r < 5; ++r) A[j][r] = tp0[j][r] * tp1[j][r];
+            } else if (n_pre >= 1) {
+                if (w & ST_PRE0_SET) {
 #pragma unroll
-                for (int j = 0; j < M; ++j)
+                    for (int j = 0; j < M; ++j)
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) A[j][r] *= tp1[j][r];
+                        for (int r = 0; r < 5; ++r) A[j][r] = tp0[j][r];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) A[j][r] *= tp0[j][r];
+                }
+                if (n_pre == 2) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) A[j][r] *= tp1[j][r];
+                }
             }
             if (mv) {
                 double acc[M][3][2];
@@ -600,21 +612,28 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                     __syncwarp(); // consumed by an issued DMMA/DMUL or sits in a register: nothing left for the TMA to race
                     release_stage(stage);
                 }
-#pragma unroll
-                for (int j = 0; j < M; ++j)
-#pragma unroll
-                    for (int r = 0; r < 5; ++r) A[j][r] = acc[j][r >> 1][r & 1];
-                if (mv == 2) {
+                // epilogue: the Hadamard products write A straight from the accumulators (a separate A = acc copy would
+                // cost 20 register moves per step on an issue port the MMAs already saturate)
+                if (mv == 2 && (w & ST_NPOST)) {
 #pragma unroll
                     for (int j = 0; j < M; ++j)
 #pragma unroll
-                        for (int r = 0; r < 5; ++r) A[j][r] *= pv[j][r];
-                }
-                if (w & ST_NPOST) {
+                        for (int r = 0; r < 5; ++r) A[j][r] = (acc[j][r >> 1][r & 1] * pv[j][r]) * vp[j][r];
+                } else if (mv == 2) {
 #pragma unroll
                     for (int j = 0; j < M; ++j)
 #pragma unroll
-                        for (int r = 0; r < 5; ++r) A[j][r] *= vp[j][r];
+                        for (int r = 0; r < 5; ++r) A[j][r] = acc[j][r >> 1][r & 1] * pv[j][r];
+                } else if (w & ST_NPOST) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) A[j][r] = acc[j][r >> 1][r & 1] * vp[j][r];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) A[j][r] = acc[j][r >> 1][r & 1];
                 }
                 if (LAZY) {
                     // the late gathers are consumed by the multiplies above; pin those before the release so that the

@@ -493,6 +493,12 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
     return SR_OK;
 }
 
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 int check_run_args(sr_ctx* c, int64_t site0, int64_t n, int64_t n_sites, const void* lnl) {
     if (!c) return SR_ERR_ARG;
     if (site0 < 0 || n < 0 || site0 + n > n_sites)
@@ -649,8 +655,16 @@ int sr_run_device(sr_ctx* c, int64_t site0, int64_t n, double* d_lnl, double* d_
     return SR_OK;
 }
 
-static int d2h(sr_ctx* c, cudaStream_t s, void* dst, const void* src, size_t bytes) {
-    CUDA_TRY(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+// Results back to the caller. Page-locked destinations (sr_host_alloc) are DMA'd asynchronously on the D2H stream, which
+// already waits for `done`. Pageable destinations are copied synchronously after the host itself has waited for `done`:
+// asynchronous copies involving pageable memory are staged by the driver and are not something to order by stream events.
+static int d2h(sr_ctx* c, cudaStream_t s, cudaEvent_t done, bool pinned, void* dst, const void* src, size_t bytes) {
+    if (pinned) {
+        CUDA_TRY(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    } else {
+        CUDA_TRY(c, cudaEventSynchronize(done));
+        CUDA_TRY(c, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    }
     return SR_OK;
 }
 
@@ -665,6 +679,7 @@ int sr_run(sr_ctx* c, int64_t site0, int64_t n, double* lnl, double* joint, sr_c
     const int64_t chunk = std::min<int64_t>(c->chunk_cols, std::max<int64_t>(n, 1));
     cudaEvent_t done_ev[2], free_ev[2];
     for (int i = 0; i < 2; ++i) { CUDA_TRY(c, cudaEventCreateWithFlags(&done_ev[i], cudaEventDisableTiming)); CUDA_TRY(c, cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming)); }
+    const bool pin_lnl = is_pinned(lnl), pin_joint = joint && is_pinned(joint), pin_compact = compact && is_pinned(compact);
     int ci = 0;
     rc = SR_OK;
     for (int64_t done = 0; done < n && rc == SR_OK; ++ci) {
@@ -679,9 +694,9 @@ int sr_run(sr_ctx* c, int64_t site0, int64_t n, double* lnl, double* joint, sr_c
         if (rc) break;
         cudaEventRecord(done_ev[b], c->stream);
         cudaStreamWaitEvent(c->s_d2h, done_ev[b], 0);
-        if ((rc = d2h(c, c->s_d2h, lnl + done, c->d_chunk_lnl[b].p, sizeof(double) * m))) break;
-        if (joint && (rc = d2h(c, c->s_d2h, joint + done * 400, c->d_chunk_joint[b].p, sizeof(double) * 400 * m))) break;
-        if (compact && (rc = d2h(c, c->s_d2h, compact + done, c->d_chunk_compact[b].p, sizeof(sr_compact) * m))) break;
+        if ((rc = d2h(c, c->s_d2h, done_ev[b], pin_lnl, lnl + done, c->d_chunk_lnl[b].p, sizeof(double) * m))) break;
+        if (joint && (rc = d2h(c, c->s_d2h, done_ev[b], pin_joint, joint + done * 400, c->d_chunk_joint[b].p, sizeof(double) * 400 * m))) break;
+        if (compact && (rc = d2h(c, c->s_d2h, done_ev[b], pin_compact, compact + done, c->d_chunk_compact[b].p, sizeof(sr_compact) * m))) break;
         cudaEventRecord(free_ev[b], c->s_d2h);
         done += m;
     }
@@ -726,6 +741,8 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
         CUDA_TRY(c, cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming));
         CUDA_TRY(c, cudaEventCreateWithFlags(&sfree_ev[i], cudaEventDisableTiming));
     }
+    const bool src_pinned = is_pinned(states);
+    const bool pin_lnl = is_pinned(lnl), pin_joint = joint && is_pinned(joint), pin_compact = compact && is_pinned(compact);
     int ci = 0;
     for (int64_t done = 0; done < n && rc == SR_OK; ++ci) {
         const int b = ci & 1;
@@ -739,7 +756,26 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
             break;
         }
         if (ci >= 2) cudaStreamWaitEvent(c->s_h2d, sfree_ev[b], 0);     // kernels of chunk ci-2 have consumed states buffer b
-        cudaError_t e = cudaMemcpy2DAsync(c->d_chunk_states[b].p, cpitch, states + site0 + done, pitch, m, n_taxa, cudaMemcpyHostToDevice, c->s_h2d);
+        const uint8_t* src = states + site0 + done;
+        int64_t src_pitch = pitch;
+        if (!src_pinned) {
+            // Pageable caller memory is never handed to an asynchronous copy (its ordering against the other streams'
+            // work is the driver's business, and it showed: rare stale state bytes at 4M+ columns). Stage the chunk in a
+            // page-locked bounce buffer on the host thread instead; the DMA then runs from pinned memory like any other.
+            const size_t need = (size_t)m * n_taxa;
+            if (c->h_bounce_cap[b] < need) {
+                if (c->h_bounce[b]) { cudaEventSynchronize(up_ev[b]); cudaFreeHost(c->h_bounce[b]); c->h_bounce[b] = nullptr; c->h_bounce_cap[b] = 0; }
+                if (cudaMallocHost(&c->h_bounce[b], need) != cudaSuccess) { cudaGetLastError(); rc = fail(c, SR_ERR_OOM, "cannot allocate the pinned staging buffer"); break; }
+                c->h_bounce_cap[b] = need;
+            } else if (ci >= 2) {
+                cudaEventSynchronize(up_ev[b]);                          // the DMA out of this bounce buffer (chunk ci-2) is done
+            }
+            uint8_t* hb = static_cast<uint8_t*>(c->h_bounce[b]);
+            for (int t = 0; t < n_taxa; ++t) memcpy(hb + (size_t)t * m, src + (size_t)t * pitch, (size_t)m);
+            src = hb;
+            src_pitch = m;
+        }
+        cudaError_t e = cudaMemcpy2DAsync(c->d_chunk_states[b].p, cpitch, src, src_pitch, m, n_taxa, cudaMemcpyHostToDevice, c->s_h2d);
         if (e != cudaSuccess) { rc = fail(c, SR_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
         sanitize_kernel<<<c->n_sm * 4, 256, 0, c->s_h2d>>>(c->d_chunk_states[b].as<uint4>(), ((size_t)cpitch * n_taxa + 512) / 16);
         cudaEventRecord(up_ev[b], c->s_h2d);
@@ -751,9 +787,9 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
         cudaEventRecord(done_ev[b], c->stream);
         cudaEventRecord(sfree_ev[b], c->stream);
         cudaStreamWaitEvent(c->s_d2h, done_ev[b], 0);
-        if ((rc = d2h(c, c->s_d2h, lnl + done, c->d_chunk_lnl[b].p, sizeof(double) * m))) break;
-        if (joint && (rc = d2h(c, c->s_d2h, joint + done * 400, c->d_chunk_joint[b].p, sizeof(double) * 400 * m))) break;
-        if (compact && (rc = d2h(c, c->s_d2h, compact + done, c->d_chunk_compact[b].p, sizeof(sr_compact) * m))) break;
+        if ((rc = d2h(c, c->s_d2h, done_ev[b], pin_lnl, lnl + done, c->d_chunk_lnl[b].p, sizeof(double) * m))) break;
+        if (joint && (rc = d2h(c, c->s_d2h, done_ev[b], pin_joint, joint + done * 400, c->d_chunk_joint[b].p, sizeof(double) * 400 * m))) break;
+        if (compact && (rc = d2h(c, c->s_d2h, done_ev[b], pin_compact, compact + done, c->d_chunk_compact[b].p, sizeof(sr_compact) * m))) break;
         cudaEventRecord(free_ev[b], c->s_d2h);
         done += m;
     }
