@@ -18,6 +18,7 @@ ap.add_argument("--warps", type=int, default=0)
 ap.add_argument("--holes", type=int, default=-1)
 ap.add_argument("--rotate", type=int, default=-1)
 ap.add_argument("--prefetch", type=int, default=-1)
+ap.add_argument("--rescale", type=int, default=0)
 ap.add_argument("--taxa", type=int, default=1000)
 ap.add_argument("--tree", default="yule")
 ap.add_argument("--ncat", type=int, default=4)
@@ -36,6 +37,8 @@ ctx = native.Context(0)
 ctx.set_option("tile_m", a.tile_m)
 if a.holes >= 0:
     ctx.set_option("holes", a.holes)
+if a.rescale:
+    ctx.set_option("rescale_every", a.rescale)
 if a.prefetch >= 0:
     ctx.set_option("prefetch", a.prefetch)
 if a.rotate >= 0:
