@@ -279,6 +279,7 @@ struct PruneParams {
     int K;
     int smem_levels;           // stack levels resident in shared memory
     int spill_levels;
+    int debug;                 // bit 0: proxy fence before the stage release; bit 1: no early barrier probe (diagnostics)
 };
 
 template <int M, int W_>
@@ -519,6 +520,24 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                     for (int r = 0; r < 5; ++r) vp[j][r] = row[r];
                 }
             }
+            // The post-MMA operands are only consumed after the burst. Pin them here so the compiler cannot sink their loads
+            // below the burst (it may move plain loads across the volatile DMMAs): the stage is released right after the
+            // burst, and a load from it that is still in flight then races the TMA refill (seen as 1-in-10 runs with a few
+            // columns off by 1e-5 at 5,000 taxa; tests/test_gpu_parity.py::*full_size*, tools/stress_big.py).
+            if (!LAZY && mv) {
+                if (w & ST_NPOST) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) asm volatile("" : "+d"(vp[j][r]));
+                }
+                if (mv == 2) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) asm volatile("" : "+d"(pv[j][r]));
+                }
+            }
             // ... products after all of them are in flight
             if (n_pre == 2 && (w & ST_PRE0_SET)) {                       // cherry: the common case, no selects
 #pragma unroll
@@ -578,9 +597,25 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                         for (int t = 0; t < 3; ++t) dmma(acc[j][t][0], acc[j][t][1], A[j][s], Bf[s * 3 + t]);
                 }
                 if (ROT && n_rot > 1) bar_arrive64(bar_pass_id);
+                if (!LAZY) {
+                    // Every read of this stage was issued before or inside the burst (>= 480 cycles ago; the pins above keep
+                    // the compiler from sinking them). Shared loads of a warp complete in order, so one instruction that reads
+                    // the registers of the LAST loads makes the scoreboard prove all of them complete before the arrive is
+                    // issued — the same contract CUTLASS's consumer_release relies on. `debug` bit 0 adds the (5 % slower)
+                    // fence.proxy.async for diagnosis.
+                    {
+                        unsigned sink;
+                        asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo, hi}, %1; mov.b64 {%0, hi}, %2; xor.b32 %0, %0, lo; }"
+                                     : "=r"(sink) : "d"(vp[M - 1][4]), "d"(pv[M - 1][4]));
+                        asm volatile("" :: "r"(sink));
+                    }
+                    if (p.debug & 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    release_stage(stage);
+                }
                 {   // probe the next stage now: the ~60-cycle TRYWAIT latency hides behind this step's epilogue
                     const uint32_t itp = it + (PREF ? 2 : 1);
-                    next_ready = mbar_test_wait(&full[itp % NSTAGE], (itp / NSTAGE) & 1);
+                    next_ready = (p.debug & 2) ? false : mbar_test_wait(&full[itp % NSTAGE], (itp / NSTAGE) & 1);
                 }
                 if (LAZY) {
                     if (w & ST_NPOST) {
@@ -608,10 +643,6 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                         }
                     }
                 }
-                if (!LAZY) {      // every read of the stage was issued before (or inside) the burst and its value has been
-                    __syncwarp(); // consumed by an issued DMMA/DMUL or sits in a register: nothing left for the TMA to race
-                    release_stage(stage);
-                }
                 // epilogue: the Hadamard products write A straight from the accumulators (a separate A = acc copy would
                 // cost 20 register moves per step on an issue port the MMAs already saturate)
                 if (mv == 2 && (w & ST_NPOST)) {
@@ -636,7 +667,7 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                         for (int r = 0; r < 5; ++r) A[j][r] = acc[j][r >> 1][r & 1];
                 }
                 if (LAZY) {
-                    // the late gathers are consumed by the multiplies above; pin those before the release so that the
+                    // the late gathers are consumed by the products above; pin those in front of the release so that the
                     // (in-order) arrive cannot be issued while a load from this stage is still in flight
 #pragma unroll
                     for (int j = 0; j < M; ++j)

@@ -71,6 +71,7 @@ struct sr_ctx {
 
     // options
     int tile_m = 2;
+    int debug = 0;
     int holes = 2;                      // pauses inside a warp's MMA burst (0..2), see kernels.cuh
     int compress = 0;                   // reduce every batch to its distinct column patterns first
     int prefetch = 0;                   // fetch the next step's first operands inside the current MMA burst
@@ -396,6 +397,7 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     p.n_steps = (int)c->steps.size() / 4;
     p.n_tiles = (int)tiles;
     p.K = c->K;
+    p.debug = c->debug;
     // kernel variants: tile_m (column tiles per warp), consumer warps, holes in the MMA burst, burst rotation
     const int hl = c->holes, rot = c->rotate;
     if (c->tile_m == 4) rc = launch_prune<4, 4, 8>(c, s, p, n);
@@ -834,6 +836,8 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
         c->last_unique = c->last_total = 0;
     } else if (k == "prefetch") {
         c->prefetch = value != 0;
+    } else if (k == "debug") {
+        c->debug = (int)value;
     } else if (k == "rotate") {
         c->rotate = value != 0;
     } else if (k == "stream_chunk_cols") {

@@ -140,9 +140,10 @@ def test_cfg4_full_size_properties(ctx):
     setup(ctx, p)
     big = np.tile(p.states, (1, 196))[:, :200_000]
     ctx.set_alignment(big)
-    r = ctx.run(want_joint=False, want_compact=True, threshold=0.5)
-    assert r["lnl"].shape == (200_000,)
-    assert np.array_equal(r["lnl"], np.tile(r["lnl"][:1024], 196)[:200_000])
+    for _ in range(4):      # repeated: this shape (matrix stream larger than L2) is the one that exposed the ring-stage races
+        r = ctx.run(want_joint=False, want_compact=True, threshold=0.5)
+        assert r["lnl"].shape == (200_000,)
+        assert np.array_equal(r["lnl"], np.tile(r["lnl"][:1024], 196)[:200_000])
     assert rel_err(r["lnl"][:1024], lnl) < TOL
     assert rel_err(r["compact"]["max_prob"][:1024], joint.max(axis=(1, 2))) < TOL
     tail = ctx.run(site0=199_000, n=1000)
