@@ -50,3 +50,38 @@ def reduce_total_lnl(local_lnl: np.ndarray, group=None) -> float:
         t = t.cuda()
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return float(t.item())
+
+
+def run_multi_context(contexts, states, want_joint=True, want_compact=False, threshold=0.5):
+    """Single-process, multi-GPU form of the sharding (what a JVM host does: one `sr_ctx` per device, each driven by its
+    own thread). `contexts` are `native.Context`s with model, rates and tree already set; columns are
+    split with `column_block`, every context streams its block from host memory, results are concatenated in column
+    order. ctypes releases the GIL during the native call, so the blocks really run concurrently."""
+    import threading
+    states = np.ascontiguousarray(states, dtype=np.uint8)
+    n_sites = states.shape[1]
+    G = len(contexts)
+    outs = [None] * G
+    errs = [None] * G
+
+    def work(g):
+        try:
+            lo, n = column_block(n_sites, G, g)
+            outs[g] = contexts[g].run_streamed(states, lo, n, want_joint=want_joint, want_compact=want_compact,
+                                               threshold=threshold) if n else None
+        except Exception as e:          # surfaced on the caller's thread
+            errs[g] = e
+
+    threads = [threading.Thread(target=work, args=(g,)) for g in range(G)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errs:
+        if e is not None:
+            raise e
+    parts = [o for o in outs if o is not None]
+    res = {"lnl": np.concatenate([o["lnl"] for o in parts]) if parts else np.empty(0)}
+    res["joint"] = np.concatenate([o["joint"] for o in parts]) if want_joint and parts else None
+    res["compact"] = np.concatenate([o["compact"] for o in parts]) if want_compact and parts else None
+    return res

@@ -329,6 +329,27 @@ def test_host_mirror_interface(ctx, example_problem):
     assert len(res) == 130 and res[13].subs[0] == "RK" and str(res[13]).startswith("Result\t14\t-7.0\tRK:1.0")
 
 
+def test_single_process_multi_context_sharding(ctx, example_problem):
+    """One process, several contexts (one per device in production; three on cuda:0 here), each on its own thread."""
+    from subrecon_b200 import sharding
+    p = example_problem
+    setup(ctx, p)
+    ref = ctx.run()
+    ctxs = [native.Context(0) for _ in range(3)]
+    try:
+        for c in ctxs:
+            c.set_model(p.model.Eval, p.model.Evec, p.model.Ievc, p.model.pi)
+            c.set_rates(p.rates)
+            c.set_tree(p.flat)
+        big = np.tile(p.states, (1, 40))
+        r = sharding.run_multi_context(ctxs, big, want_joint=True, want_compact=True)
+        assert np.array_equal(r["lnl"], np.tile(ref["lnl"], 40)) and np.array_equal(r["joint"][:130], ref["joint"])
+        assert np.array_equal(r["compact"]["lnl"], r["lnl"])
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_error_behaviour(ctx, example_problem):
     p = example_problem
     fresh = native.Context(0)
