@@ -304,6 +304,32 @@ def test_leaf_as_root_child(ctx):
     assert np.count_nonzero(r["joint"][0].sum(axis=1) > 0) == 1         # state at A is the observed tip state
 
 
+def test_degenerate_shapes(ctx):
+    """Two-taxon tree (both root children are tips, K=1 as the reference requires), K=16 rate classes, a single column."""
+    model = oracle.OracleModel("JTT")
+    tree = treeio.parse_newick("(a:0.1,b:0.2);")
+    flat = treeio.flatten_tree(tree)
+    states = treeio.encode_alignment(["AR-W", "AK-C"])
+    lnl, joint = oracle.run(flat, states, model, np.array([1.0]))
+    ctx.set_option("tile_m", 2)
+    ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
+    ctx.set_rates(np.array([1.0]))
+    ctx.set_tree(flat)
+    ctx.set_alignment(states)
+    r = ctx.run()
+    assert lnl_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
+    p = synthetic(2, 64)
+    rates = oracle.gamma_rates(16, 0.3)
+    lnl, joint = oracle.run(p.flat, p.states, p.model, rates)
+    setup(ctx, p)
+    ctx.set_rates(rates)
+    r = ctx.run()
+    assert rel_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
+    one = ctx.run(site0=63, n=1)
+    assert rel_err(one["lnl"], lnl[63:]) < TOL and rel_err(one["joint"], joint[63:]) < TOL
+    ctx.set_rates(p.rates)
+
+
 def test_compact_matches_site_result_scan(ctx, example_problem):
     p = example_problem
     setup(ctx, p)
