@@ -110,7 +110,8 @@ void sr_host_free(void *p);
 /* Tuning / introspection. Options: "tile_m" (MMA column tiles per warp: 2 or 4), "warps" (consumer warps per
  * CTA: 8, 11, 15, or 12 = experimental variant without a producer warp), "holes" (0..2 pauses inside a warp's MMA burst), "rotate" (0/1 burst hand-off between the warps of
  * an SM sub-partition), "compress_patterns" (0/1: compute each distinct column pattern of a batch once and copy the
- * result to its duplicates; off by default), "prefetch" (experimental), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage), "profile"
+ * result to its duplicates; off by default), "prefetch" (experimental), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage), "stream_taper" (0/1: short pipeline
+ * chunks at both ends of a streamed run, on by default), "profile"
  * (0/1: record per-kernel events), "rescale_every" (edges between power-of-two rescalings). */
 int sr_set_option(sr_ctx *ctx, const char *name, int64_t value);
 int sr_get_profile(sr_ctx *ctx, sr_profile *out);     /* synchronises the context's streams */

@@ -78,6 +78,7 @@ struct sr_ctx {
     int rotate = 1;                     // named-barrier burst rotation among the warps of an SM sub-partition
     int warps = 11;                     // consumer warps per CTA (tile_m == 2 only: 8, 11 or 15)
     int64_t chunk_cols = 1 << 20;       // resident runs: columns per launch
+    bool stream_taper = true;            // streamed runs: short chunks at both ends of the pipeline
     int64_t stream_chunk_cols = 1 << 17; // streamed runs: columns per pipeline stage (H2D | kernels | D2H overlap)
     int rescale_every = 8;
     bool profile = false;
@@ -745,18 +746,43 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
     }
     const bool src_pinned = is_pinned(states);
     const bool pin_lnl = is_pinned(lnl), pin_joint = joint && is_pinned(joint), pin_compact = compact && is_pinned(compact);
-    int ci = 0;
-    for (int64_t done = 0; done < n && rc == SR_OK; ++ci) {
-        const int b = ci & 1;
-        const int64_t m = std::min(n - done, chunk);
+    // Chunk sizes: full chunks in the middle, a ramp of short ones at both ends. The pipeline's exposed time is the
+    // upload of the first chunk plus the download of the last one (3200 B per column of joint output), so those two are
+    // made an eighth of a full chunk; each neighbour doubles, which keeps every copy hidden behind the kernels next to it.
+    std::vector<int64_t> sizes;
+    {
+        const int64_t S = (int64_t)c->warps * c->tile_m * 8;
+        int64_t g = c->n_sm, b = std::max(1, c->K);
+        while (b) { const int64_t t = g % b; g = b; b = t; }
+        const int64_t unit = (c->n_sm / g) * S;
+        int64_t ramp[3] = {0, 0, 0}, ramp_sum = 0;
+        if (c->stream_taper && chunk >= 8 * unit)
+            for (int i = 0; i < 3; ++i) { ramp[i] = std::max<int64_t>(unit, (chunk >> (3 - i)) / unit * unit); ramp_sum += ramp[i]; }
+        int64_t left = n;
+        if (ramp_sum && n >= 2 * ramp_sum + chunk) {
+            for (int i = 0; i < 3; ++i) { sizes.push_back(ramp[i]); left -= ramp[i]; }
+            while (left - ramp_sum >= chunk) { sizes.push_back(chunk); left -= chunk; }
+            if (left > ramp_sum) { sizes.push_back(left - ramp_sum); left = ramp_sum; }
+            for (int i = 2; i >= 0; --i) { sizes.push_back(ramp[i]); left -= ramp[i]; }
+        } else {
+            while (left > 0) { const int64_t m = std::min(left, chunk); sizes.push_back(m); left -= m; }
+        }
+    }
+    const int64_t mmax = std::min(n, chunk);
+    for (int b = 0; b < 2 && rc == SR_OK; ++b) {
         if (c->d_chunk_states[b].reserve((size_t)cpitch * n_taxa + 512) != cudaSuccess ||
-            c->d_chunk_lnl[b].reserve(sizeof(double) * m) != cudaSuccess ||
-            (joint && c->d_chunk_joint[b].reserve(sizeof(double) * 400 * m) != cudaSuccess) ||
-            (compact && c->d_chunk_compact[b].reserve(sizeof(sr_compact) * m) != cudaSuccess)) {
+            c->d_chunk_lnl[b].reserve(sizeof(double) * mmax) != cudaSuccess ||
+            (joint && c->d_chunk_joint[b].reserve(sizeof(double) * 400 * mmax) != cudaSuccess) ||
+            (compact && c->d_chunk_compact[b].reserve(sizeof(sr_compact) * mmax) != cudaSuccess)) {
             cudaGetLastError();
             rc = fail(c, SR_ERR_OOM, "device OOM (pipeline chunk buffers)");
-            break;
         }
+        if (sizes.size() < 2) break;
+    }
+    int64_t done = 0;
+    for (size_t ci = 0; ci < sizes.size() && rc == SR_OK; ++ci) {
+        const int b = (int)(ci & 1);
+        const int64_t m = sizes[ci];
         if (ci >= 2) cudaStreamWaitEvent(c->s_h2d, sfree_ev[b], 0);     // kernels of chunk ci-2 have consumed states buffer b
         const uint8_t* src = states + site0 + done;
         int64_t src_pitch = pitch;
@@ -764,7 +790,7 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
             // Pageable caller memory is never handed to an asynchronous copy (its ordering against the other streams'
             // work is the driver's business, and it showed: rare stale state bytes at 4M+ columns). Stage the chunk in a
             // page-locked bounce buffer on the host thread instead; the DMA then runs from pinned memory like any other.
-            const size_t need = (size_t)m * n_taxa;
+            const size_t need = (size_t)mmax * n_taxa;                   // sized for a full chunk once, not per ramp step
             if (c->h_bounce_cap[b] < need) {
                 if (c->h_bounce[b]) { cudaEventSynchronize(up_ev[b]); cudaFreeHost(c->h_bounce[b]); c->h_bounce[b] = nullptr; c->h_bounce_cap[b] = 0; }
                 if (cudaMallocHost(&c->h_bounce[b], need) != cudaSuccess) { cudaGetLastError(); rc = fail(c, SR_ERR_OOM, "cannot allocate the pinned staging buffer"); break; }
@@ -843,6 +869,8 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     } else if (k == "stream_chunk_cols") {
         if (value < 256) return fail(c, SR_ERR_ARG, "stream_chunk_cols must be >= 256");
         c->stream_chunk_cols = (value + 255) / 256 * 256;
+    } else if (k == "stream_taper") {
+        c->stream_taper = value != 0;
     } else if (k == "profile") {
         c->profile = value != 0;
     } else if (k == "rescale_every") {
