@@ -221,6 +221,21 @@ def test_ragged_offsets_and_chunks(ctx, example_problem):
     assert np.array_equal(one["lnl"], st["lnl"]) and np.array_equal(one["joint"], st["joint"])
     assert np.array_equal(part["lnl"], one["lnl"][131:831]) and np.array_equal(part["joint"], one["joint"][131:831])
     assert rel_err(one["lnl"], np.tile(lnl, 9)) < TOL
+    # the streamed pipeline's ramp of short chunks at both ends (needs >= 8 kernel waves per chunk to engage) and an
+    # odd-sized middle remainder: same bits as uniform chunks and as the resident path
+    wide = np.tile(p.states, (1, 1201))[:, :156001]
+    try:
+        ctx.set_option("stream_chunk_cols", 53000)
+        tapered = ctx.run_streamed(wide, want_joint=True, want_compact=True, threshold=0.3)
+        ctx.set_option("stream_taper", 0)
+        uniform = ctx.run_streamed(wide, want_joint=True, want_compact=True, threshold=0.3)
+    finally:
+        ctx.set_option("stream_taper", 1)
+        ctx.set_option("stream_chunk_cols", 1 << 17)
+    for k in ("lnl", "joint"):
+        assert np.array_equal(tapered[k], uniform[k])
+        assert np.array_equal(tapered[k][:1170], one[k]) and np.array_equal(tapered[k][-131:], tapered[k][:131])
+    assert tapered["compact"].tobytes() == uniform["compact"].tobytes()
 
 
 def test_column_pattern_compression(ctx, example_problem):
