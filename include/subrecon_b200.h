@@ -84,7 +84,11 @@ int sr_set_tree(sr_ctx *ctx, int32_t n_nodes, const int32_t *child_off, const in
                 const double *blen, const int32_t *leaf_row, int32_t root);
 
 /* Replaces `alignment.getStateBySequenceName(name, site)` (molevo/AdvancedAlignmentAminoAcid.java:34-40):
- * states[taxon*pitch + site], 0..19 or SR_STATE_MISSING, uploaded once and kept in HBM. */
+ * states[taxon*pitch + site], 0..19 or SR_STATE_MISSING, uploaded once and kept in HBM.
+ * With option "input_chars" = 1 the bytes are the alignment's residue LETTERS instead (what PAL's
+ * `SimpleAlignment.getData(seq, site)` returns, Latin-1) and the device translates them exactly as
+ * `AminoAcids::getStateImpl` does (either case, PAL order; gaps, '?', '*', B J O U X Z and any other byte are
+ * missing data) — the host then needs no per-cell encode loop at all. Applies to sr_run_streamed as well. */
 int sr_set_alignment(sr_ctx *ctx, int32_t n_taxa, int64_t n_sites, const uint8_t *states, int64_t pitch);
 
 /* Replaces the submit/join loop (SubRecon.java:112-142) for columns [site0, site0+n) of the resident
@@ -111,7 +115,9 @@ void sr_host_free(void *p);
  * CTA: 8, 11, 15, or 12 = experimental variant without a producer warp), "holes" (0..2 pauses inside a warp's MMA burst), "rotate" (0/1 burst hand-off between the warps of
  * an SM sub-partition), "compress_patterns" (0/1: compute each distinct column pattern of a batch once and copy the
  * result to its duplicates; off by default), "prefetch" (experimental), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage), "stream_taper" (0/1: short pipeline
- * chunks at both ends of a streamed run, on by default), "profile"
+ * chunks at both ends of a streamed run, on by default), "input_chars" (0/1: alignment bytes are residue letters, see
+ * sr_set_alignment), "realloc" (0/1, experimental: producer warp on re-allocated registers, 12 x tile_m 2 or
+ * 8 x tile_m 4 consumer warps), "profile"
  * (0/1: record per-kernel events), "rescale_every" (edges between power-of-two rescalings). */
 int sr_set_option(sr_ctx *ctx, const char *name, int64_t value);
 int sr_get_profile(sr_ctx *ctx, sr_profile *out);     /* synchronises the context's streams */

@@ -177,6 +177,32 @@ __global__ void __launch_bounds__(256) sanitize_kernel(uint4* __restrict__ v, si
     }
 }
 
+// Same pass for RESIDUE CHARACTERS ("input_chars"): the bytes are the alignment's letters as PAL holds them
+// (`SimpleAlignment.getData` = `String.charAt`), translated the way `AminoAcids::getStateImpl` does:
+// letters of either case A0 R1 N2 D3 C4 Q5 E6 G7 H8 I9 L10 K11 M12 F13 P14 S15 T16 W17 Y18 V19; gaps, '?', '*',
+// B J O U X Z and every other byte are outside 0..19 for the reference and therefore missing data (20) here. This is
+// the reference's per-cell `getStateBySequenceName` (molevo/AdvancedAlignmentAminoAcid.java:34-40) as one streaming pass.
+__global__ void __launch_bounds__(256) encode_chars_kernel(uint4* __restrict__ v, size_t n16) {
+    __shared__ uint8_t lut[256];
+    {
+        //                      A  B   C  D  E  F   G  H  I  J   K   L   M   N  O   P   Q  R  S   T   U   V   W   X   Y   Z
+        const uint8_t pos[26] = {0, 20, 4, 3, 6, 13, 7, 8, 9, 20, 11, 10, 12, 2, 20, 14, 5, 1, 15, 16, 20, 19, 17, 20, 18, 20};
+        const int c = threadIdx.x, lower = c | 0x20;
+        const bool letter = (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z');
+        lut[c] = letter ? pos[lower - 'a'] : (uint8_t)20;
+    }
+    __syncthreads();
+    auto tr = [&](unsigned x) {
+        return (unsigned)lut[x & 0xff] | ((unsigned)lut[(x >> 8) & 0xff] << 8) | ((unsigned)lut[(x >> 16) & 0xff] << 16) |
+               ((unsigned)lut[x >> 24] << 24);
+    };
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 x = v[i];
+        x.x = tr(x.x); x.y = tr(x.y); x.z = tr(x.z); x.w = tr(x.w);
+        v[i] = x;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- column patterns
 // Identical alignment columns have identical results, so a batch can be reduced to its distinct column patterns
 // (the reference recomputes every column, SubRecon.java:112-116). A pattern is identified by a 128-bit
@@ -280,7 +306,15 @@ struct PruneParams {
     int smem_levels;           // stack levels resident in shared memory
     int spill_levels;
     int debug;                 // bit 0: proxy fence before the stage release; bit 1: no early barrier probe (diagnostics)
+    unsigned* timeline;        // SR_TIMELINE builds only (tools/timeline.py): [warp][SR_TL_STEPS][8] clock stamps of CTA 0
 };
+
+#ifdef SR_TIMELINE
+constexpr int SR_TL_STEPS = 1024;
+#define SR_TL(k) do { if (blockIdx.x == 0 && lane == 0 && it < (uint32_t)SR_TL_STEPS) p.timeline[((size_t)warp * SR_TL_STEPS + it) * 8 + (k)] = (unsigned)clock(); } while (0)
+#else
+#define SR_TL(k) do { } while (0)
+#endif
 
 template <int M, int W_>
 struct PruneCfg {
@@ -306,8 +340,34 @@ __device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive 
 // released it; it only blocks when it reaches a position it has not requested yet. All W_ warps of the CTA are consumers,
 // so each SM sub-partition gets the same number of MMA warps (with a producer warp, its sub-partition runs one consumer
 // short and its tensor pipe idles a third of the time).
-template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false>
-__global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(PruneParams p) {
+//
+// RA: register re-allocation (setmaxnreg). A sub-partition's register file holds three warps of 168 registers, so a
+// producer warp next to W_ = 11 consumers leaves its sub-partition one MMA warp short (tensor pipe ~53 % busy there
+// against ~79 % on the other three). With RA the CTA is launched as whole warpgroups and the last one (the producer plus
+// three warps that exit at once) shrinks to 32 registers, which frees exactly enough for the consumers to grow:
+//   M = 2: 16 warps x 128 at launch -> 12 consumers x 160 (three MMA warps on every sub-partition, producer as a light fourth)
+//   M = 4: 12 warps x 168 at launch ->  8 consumers x 232 (two MMA warps per sub-partition, four column tiles each)
+// burst holes: bit s of the mask = pause (just-in-time fragment fetch) before k-step s
+__host__ __device__ constexpr int hole_mask(int holes) {
+    if (holes == 0) return 0;
+    if (holes == 1) return 1 << 3;
+    if (holes == 2) return (1 << 2) | (1 << 4);
+    int m = 0;
+    while (holes > 0) { m |= 1 << (holes % 10); holes /= 10; }
+    return m & 0x1e;
+}
+__host__ __device__ constexpr int next_hole(int mask, int s) {          // first hole after k-step s, 5 if none
+    for (int t = s + 1; t < 5; ++t) if ((mask >> t) & 1) return t;
+    return 5;
+}
+__host__ __device__ constexpr int first_hole(int mask) { return next_hole(mask, 0); }
+__host__ __device__ constexpr int pairs_before(int kstep) { return kstep >= 5 ? 8 : (3 * kstep + 1) / 2; }   // 16-byte fragment pairs covering k-steps < kstep
+
+constexpr int prune_threads(int w, bool inl, bool ra) { return ra ? (w + 4) * 32 : (w + (inl ? 0 : 1)) * 32; }
+
+template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false, bool RA = false>
+__global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(PruneParams p) {
+    static_assert(!RA || (!INL && ((W_ == 12 && M == 2) || (W_ == 8 && M == 4))), "register re-allocation is laid out for 12 x M=2 or 8 x M=4 consumer warps");
     using Cfg = PruneCfg<M, W_>;
     constexpr int W = Cfg::W;
     constexpr int S = Cfg::S;
@@ -350,12 +410,24 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
         if (n_leaf > 2) bulk_g2s(dst + Cfg::STATES_OFF + 2 * S, st + (int64_t)d.w * p.pitch, S, &full[stage]);
     };
 
-    if (!INL && warp == W) {
-        // ===== producer: one lane streams every step's matrices (and tip states) into the ring =====
+    // ===== producer: one lane streams every step's matrices (and tip states) into the ring =====
+    auto produce = [&]() {
         if (lane == 0) {
             for (int item = blockIdx.x; item < n_items; item += gridDim.x)
                 for (int step = 0; step < p.n_steps; ++step, ++it) issue_step(it, item, __ldg(p.steps + step), __ldg(p.step_off + step), true);
         }
+    };
+    if (RA) {
+        // one structural split, so that the register allocator sees which code runs under which budget
+        if (warp >= W) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+            if (warp == W) produce();                 // warps 13..15 only existed to donate their registers
+            return;
+        }
+        if (W_ == 12) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    } else if (!INL && warp == W) {
+        produce();
         return;
     }
 
@@ -418,12 +490,9 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
         int sp = 0;
         int w_next = __ldg(&p.steps[0].x);
         bool next_ready = false;           // result of an early, non-blocking probe of a later stage's full barrier
-        // HOLES encodes before which k-steps the burst pauses: 0 none, 1 -> {3}, 2 -> {2,4}, two digits ab -> {a,b}
-        constexpr int H1 = (HOLES == 0) ? 9 : (HOLES == 1 ? 3 : (HOLES == 2 ? 2 : HOLES / 10));
-        constexpr int H2 = (HOLES == 0 || HOLES == 1) ? 9 : (HOLES == 2 ? 4 : HOLES % 10);
-        constexpr int PAIRS0 = (H1 >= 5) ? 8 : (3 * H1 + 1) / 2;          // pairs covering fragments [0, 3*H1)
-        constexpr int PAIRS1 = (H2 >= 5) ? 8 : (3 * H2 + 1) / 2;          // ... [0, 3*H2)
-        constexpr int FIRST = PAIRS0;                                      // fragment pairs fetched before the burst
+        // HOLES encodes before which k-steps (1..4) the burst pauses: 0 none, 1 -> {3}, 2 -> {2,4}, digits "ab.." -> {a,b,..}
+        constexpr int HMASK = hole_mask(HOLES);
+        constexpr int FIRST = pairs_before(next_hole(HMASK, 0));           // fragment pairs fetched before the burst
         int s0[M], s1[M], s2[M];
         double Bf[16];
         if (PREF) {
@@ -444,6 +513,7 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
             const int w = w_next;
             const bool has_next = step + 1 < p.n_steps;
             if (has_next) w_next = __ldg(&p.steps[step + 1].x);
+            SR_TL(0);                                   // step begins
             if (INL) my_refill(/*block=*/my_pos <= it);
             const int mv = w & ST_MV_MASK, n_pre = (w >> ST_NPRE_SHIFT) & 3;
             const unsigned char* stg = stages + stage * STAGE_BYTES;
@@ -461,6 +531,7 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                 if (!next_ready) mbar_wait(&full[stage], ph);
             }
             next_ready = false;
+            SR_TL(1);                                   // stage has landed
 
             // ---- all shared-memory reads of the step are issued up front
             if (!PREF) {
@@ -546,6 +617,9 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                     for (int r = 0; r < 5; ++r) A[j][r] = tp0[j][r] * tp1[j][r];
             } else if (n_pre >= 1) {
                 if (w & ST_PRE0_SET) {
+                    // (the empty asm keeps this a real branch: if-converted, "A = tp0, then maybe A = tp0 * A_old" makes
+                    // the old and the new A live at once, and every step then starts with 20 register moves)
+                    asm volatile("");
 #pragma unroll
                     for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -563,25 +637,27 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                         for (int r = 0; r < 5; ++r) A[j][r] *= tp1[j][r];
                 }
             }
+            double acc[M][3][2];
             if (mv) {
-                double acc[M][3][2];
 #pragma unroll
                 for (int j = 0; j < M; ++j)
 #pragma unroll
                     for (int t = 0; t < 3; ++t) { acc[j][t][0] = 0.0; acc[j][t][1] = 0.0; }
+                SR_TL(2);                               // operands requested, ready to burst
                 if (ROT && n_rot > 1) {          // rotation: burst only after the previous warp of this sub-partition issued its last DMMA
                     if (!first_burst) bar_sync64(bar_wait_id);
                     first_burst = false;
                 }
+                SR_TL(3);                               // burst starts
 #pragma unroll
                 for (int s = 0; s < 5; ++s) {
                     // just-in-time fragment fetch: the pairs the next chunk needs are loaded only now, so the warp pauses
-                    if (s == H1 || s == H2) {
+                    if ((HMASK >> s) & 1) {
                         asm volatile("" ::: "memory");
-                        const int lo = (s == H1) ? PAIRS0 : PAIRS1, hi = (s == H1) ? PAIRS1 : 8;
+                        const int lo = pairs_before(s), hi = pairs_before(next_hole(HMASK, s));
 #pragma unroll
                         for (int i = lo; i < hi; ++i) { const double2 v = frag[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
-                        if (PREF && s == H1 && has_next) {
+                        if (PREF && s == first_hole(HMASK) && has_next) {
                             // fragments 0..5 are dead (k-steps 0,1 issued): refill them, and the tip state codes, for step+1
                             const double2* fragn = reinterpret_cast<const double2*>(stgn) + lane;
                             const unsigned char* stbn = stgn + st_lane_off;
@@ -597,6 +673,7 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                         for (int t = 0; t < 3; ++t) dmma(acc[j][t][0], acc[j][t][1], A[j][s], Bf[s * 3 + t]);
                 }
                 if (ROT && n_rot > 1) bar_arrive64(bar_pass_id);
+                SR_TL(4);                               // last DMMA issued
                 if (!LAZY) {
                     // Every read of this stage was issued before or inside the burst (>= 480 cycles ago; the pins above keep
                     // the compiler from sinking them). Shared loads of a warp complete in order, so one instruction that reads
@@ -643,8 +720,10 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                         }
                     }
                 }
-                // epilogue: the Hadamard products write A straight from the accumulators (a separate A = acc copy would
-                // cost 20 register moves per step on an issue port the MMAs already saturate)
+                SR_TL(5);                               // stage released, next stage probed
+                // epilogue: the Hadamard products write A (the registers the next burst reads its operand from) straight
+                // from the accumulators. A plain MV (no sibling, no tip) has no product to do that move for free: its result
+                // stays in the accumulator registers and the step's tail below works on those (see `finish`).
                 if (mv == 2 && (w & ST_NPOST)) {
 #pragma unroll
                     for (int j = 0; j < M; ++j)
@@ -660,11 +739,6 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                     for (int j = 0; j < M; ++j)
 #pragma unroll
                         for (int r = 0; r < 5; ++r) A[j][r] = acc[j][r >> 1][r & 1] * vp[j][r];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < M; ++j)
-#pragma unroll
-                        for (int r = 0; r < 5; ++r) A[j][r] = acc[j][r >> 1][r & 1];
                 }
                 if (LAZY) {
                     // the late gathers are consumed by the products above; pin those in front of the release so that the
@@ -696,6 +770,11 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
 #pragma unroll
                 for (int j = 0; j < M; ++j) { s0[j] = sn0[j]; s1[j] = sn1[j]; s2[j] = sn2[j]; }
             }
+            SR_TL(6);                                   // epilogue products issued
+            // rescale / push / store of the step's result, wherever it lives: in A, or (plain MV) still in the accumulators.
+            // Two instantiations instead of a copy: 20 register moves per step were 6 % of the instructions a warp issues,
+            // on an issue port the MMAs already saturate.
+            auto finish = [&](auto&& at) {          // at(j, r): reference to entry r of column tile j
             if (w & STF_ANY) {
                 if (w & STF_RESCALE) {
                     // Power-of-two rescale done entirely in the integer pipe (the FP64 pipe is the one the MMAs need):
@@ -703,17 +782,17 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                     // is a subtraction in the exponent field. Entries more than 2^-1000 below the maximum flush to 0.
 #pragma unroll
                     for (int j = 0; j < M; ++j) {
-                        int hmx = max(max(max(__double2hiint(A[j][0]), __double2hiint(A[j][1])),
-                                          max(__double2hiint(A[j][2]), __double2hiint(A[j][3]))), __double2hiint(A[j][4]));
+                        int hmx = max(max(max(__double2hiint(at(j, 0)), __double2hiint(at(j, 1))),
+                                          max(__double2hiint(at(j, 2)), __double2hiint(at(j, 3)))), __double2hiint(at(j, 4)));
                         hmx = max(hmx, __shfl_xor_sync(0xffffffffu, hmx, 1));
                         hmx = max(hmx, __shfl_xor_sync(0xffffffffu, hmx, 2));
                         const int e = (hmx >> 20) & 0x7ff;
                         const int delta = (e - 1023) << 20;
 #pragma unroll
                         for (int r = 0; r < 5; ++r) {
-                            const int hi = __double2hiint(A[j][r]);
+                            const int hi = __double2hiint(at(j, r));
                             const int nh = hi - delta;
-                            A[j][r] = (e != 0 && nh >= 0x00100000) ? __hiloint2double(nh, __double2loint(A[j][r])) : (e != 0 ? 0.0 : A[j][r]);
+                            at(j, r) = (e != 0 && nh >= 0x00100000) ? __hiloint2double(nh, __double2loint(at(j, r))) : (e != 0 ? 0.0 : at(j, r));
                         }
                         if (e != 0) cnt[j] += e - 1023;
                     }
@@ -724,13 +803,13 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
 #pragma unroll
                         for (int j = 0; j < M; ++j)
 #pragma unroll
-                            for (int r = 0; r < 5; ++r) dst[(j * 5 + r) * 32] = A[j][r];
+                            for (int r = 0; r < 5; ++r) dst[(j * 5 + r) * 32] = at(j, r);
                     } else {
                         double* dst = spill_base + (size_t)(sp - p.smem_levels) * TILE_DOUBLES + lane;
 #pragma unroll
                         for (int j = 0; j < M; ++j)
 #pragma unroll
-                            for (int r = 0; r < 5; ++r) __stcg(dst + (j * 5 + r) * 32, A[j][r]);
+                            for (int r = 0; r < 5; ++r) __stcg(dst + (j * 5 + r) * 32, at(j, r));
                     }
                     ++sp;
                 }
@@ -741,11 +820,24 @@ __global__ void __launch_bounds__((W_ + (INL ? 0 : 1)) * 32, 1) prune_kernel(Pru
                         const int64_t col = (int64_t)tile * S + warp * (M * 8) + j * 8 + g;
                         double* dst = p.rootpart + (((size_t)which * p.K + k) * p.ncp + col) * NS + q * 5;
 #pragma unroll
-                        for (int r = 0; r < 5; ++r) dst[r] = A[j][r];
+                        for (int r = 0; r < 5; ++r) dst[r] = at(j, r);
                         if (which == 1 && q == 0) p.rootexp[(size_t)k * p.ncp + col] = cnt[j];
                     }
                 }
             }
+            };
+            if (mv == 1 && !(w & ST_NPOST)) {
+                finish([&](int j, int r) -> double& { return acc[j][r >> 1][r & 1]; });
+                if (!(w & (STF_PUSH | STF_STORE_A | STF_STORE_B))) {     // the next step continues this partial (unary chains)
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) A[j][r] = acc[j][r >> 1][r & 1];
+                }
+            } else {
+                finish([&](int j, int r) -> double& { return A[j][r]; });
+            }
+            SR_TL(7);                                   // step ends
         }
     }
 }

@@ -68,15 +68,20 @@ struct sr_ctx {
     int32_t max_leaf_row = -1;
     double root_blen = 0.0;
     bool sched_dirty = true, p_dirty = true;
+#ifdef SR_TIMELINE
+    DevBuf d_timeline;
+#endif
 
     // options
     int tile_m = 2;
     int debug = 0;
     int holes = 2;                      // pauses inside a warp's MMA burst (0..2), see kernels.cuh
+    bool input_chars = false;           // alignment bytes are residue letters, translated on the device
     int compress = 0;                   // reduce every batch to its distinct column patterns first
     int prefetch = 0;                   // fetch the next step's first operands inside the current MMA burst
     int rotate = 1;                     // named-barrier burst rotation among the warps of an SM sub-partition
-    int warps = 11;                     // consumer warps per CTA (tile_m == 2 only: 8, 11 or 15)
+    int warps = 12;                     // consumer warps per CTA (tile_m == 2: 8, 11, 12 or 15)
+    bool realloc = true;                // producer warp on re-allocated registers (setmaxnreg): 12 x tile_m 2 or 8 x tile_m 4 consumers
     int64_t chunk_cols = 1 << 20;       // resident runs: columns per launch
     bool stream_taper = true;            // streamed runs: short chunks at both ends of the pipeline
     int64_t stream_chunk_cols = 1 << 17; // streamed runs: columns per pipeline stage (H2D | kernels | D2H overlap)
@@ -346,7 +351,7 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     return SR_OK;
 }
 
-template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false>
+template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false, bool RA = false>
 int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     using Cfg = PruneCfg<M, W>;
     const int fixed = NSTAGE * Cfg::STAGE_BYTES + prune_bar_bytes(NSTAGE);
@@ -361,10 +366,10 @@ int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     p.spill_levels = spill_levels;
     p.spill = c->d_spill.as<double>();
     const int smem = fixed + levels * Cfg::LEVEL_BYTES;
-    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT, PREF, INL>;
+    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT, PREF, INL, RA>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prof_begin(c, s, 1, cols);
-    kern<<<grid, (W + (INL ? 0 : 1)) * 32, smem, s>>>(p);
+    kern<<<grid, prune_threads(W, INL, RA), smem, s>>>(p);
     prof_end(c, s);
     CUDA_TRY(c, cudaGetLastError());
     return SR_OK;
@@ -399,9 +404,22 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     p.n_tiles = (int)tiles;
     p.K = c->K;
     p.debug = c->debug;
+#ifdef SR_TIMELINE
+    if (c->d_timeline.reserve(sizeof(unsigned) * 16 * SR_TL_STEPS * 8) != cudaSuccess) return fail(c, SR_ERR_OOM, "timeline buffer");
+    cudaMemsetAsync(c->d_timeline.p, 0, sizeof(unsigned) * 16 * SR_TL_STEPS * 8, s);
+    p.timeline = c->d_timeline.as<unsigned>();
+#endif
     // kernel variants: tile_m (column tiles per warp), consumer warps, holes in the MMA burst, burst rotation
     const int hl = c->holes, rot = c->rotate;
-    if (c->tile_m == 4) rc = launch_prune<4, 4, 8>(c, s, p, n);
+    if (c->tile_m == 4 && c->realloc) rc = rot ? launch_prune<4, 4, 8, 2, true, false, false, true>(c, s, p, n) : launch_prune<4, 4, 8, 0, false, false, false, true>(c, s, p, n);
+    else if (c->tile_m == 4) rc = launch_prune<4, 4, 8>(c, s, p, n);
+    else if (c->warps == 12 && c->realloc && rot && hl == 0) rc = launch_prune<2, 4, 12, 0, true, false, false, true>(c, s, p, n);
+    else if (c->warps == 12 && c->realloc && rot && hl == 1) rc = launch_prune<2, 4, 12, 1, true, false, false, true>(c, s, p, n);
+    else if (c->warps == 12 && c->realloc && rot && hl == 13) rc = launch_prune<2, 4, 12, 13, true, false, false, true>(c, s, p, n);
+    else if (c->warps == 12 && c->realloc && rot && hl == 123) rc = launch_prune<2, 4, 12, 123, true, false, false, true>(c, s, p, n);
+    else if (c->warps == 12 && c->realloc && rot && hl == 234) rc = launch_prune<2, 4, 12, 234, true, false, false, true>(c, s, p, n);
+    else if (c->warps == 12 && c->realloc && rot && hl == 1234) rc = launch_prune<2, 4, 12, 1234, true, false, false, true>(c, s, p, n);
+    else if (c->warps == 12 && c->realloc) rc = rot ? launch_prune<2, 4, 12, 2, true, false, false, true>(c, s, p, n) : launch_prune<2, 4, 12, 2, false, false, false, true>(c, s, p, n);
     else if (c->warps == 12) rc = rot ? launch_prune<2, 4, 12, 2, true, false, true>(c, s, p, n) : launch_prune<2, 4, 12, 2, false, false, true>(c, s, p, n);
     else if (c->warps == 8) rc = rot ? launch_prune<2, 4, 8, 2, true>(c, s, p, n) : launch_prune<2, 4, 8, 0, false>(c, s, p, n);
     else if (c->warps == 15) rc = rot ? launch_prune<2, 4, 15, 2, true>(c, s, p, n) : launch_prune<2, 4, 15, 0, false>(c, s, p, n);
@@ -630,7 +648,8 @@ int sr_set_alignment(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* 
     CUDA_TRY(c, cudaMemsetAsync(c->d_states.p, SR_STATE_MISSING, (size_t)dp * n_taxa + 512, c->stream));
     if (n_sites > 0)
         CUDA_TRY(c, cudaMemcpy2DAsync(c->d_states.p, dp, states, pitch, n_sites, n_taxa, cudaMemcpyHostToDevice, c->stream));
-    sanitize_kernel<<<c->n_sm * 8, 256, 0, c->stream>>>(c->d_states.as<uint4>(), ((size_t)dp * n_taxa + 512) / 16);
+    if (c->input_chars) encode_chars_kernel<<<c->n_sm * 8, 256, 0, c->stream>>>(c->d_states.as<uint4>(), ((size_t)dp * n_taxa + 512) / 16);
+    else sanitize_kernel<<<c->n_sm * 8, 256, 0, c->stream>>>(c->d_states.as<uint4>(), ((size_t)dp * n_taxa + 512) / 16);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->aln_taxa = n_taxa;
@@ -805,7 +824,8 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
         }
         cudaError_t e = cudaMemcpy2DAsync(c->d_chunk_states[b].p, cpitch, src, src_pitch, m, n_taxa, cudaMemcpyHostToDevice, c->s_h2d);
         if (e != cudaSuccess) { rc = fail(c, SR_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
-        sanitize_kernel<<<c->n_sm * 4, 256, 0, c->s_h2d>>>(c->d_chunk_states[b].as<uint4>(), ((size_t)cpitch * n_taxa + 512) / 16);
+        if (c->input_chars) encode_chars_kernel<<<c->n_sm * 4, 256, 0, c->s_h2d>>>(c->d_chunk_states[b].as<uint4>(), ((size_t)cpitch * n_taxa + 512) / 16);
+        else sanitize_kernel<<<c->n_sm * 4, 256, 0, c->s_h2d>>>(c->d_chunk_states[b].as<uint4>(), ((size_t)cpitch * n_taxa + 512) / 16);
         cudaEventRecord(up_ev[b], c->s_h2d);
         cudaStreamWaitEvent(c->stream, up_ev[b], 0);
         if (ci >= 2) cudaStreamWaitEvent(c->stream, free_ev[b], 0);     // output buffers b drained
@@ -845,21 +865,29 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     if (k == "tile_m") {
         if (value != 2 && value != 4) return fail(c, SR_ERR_ARG, "tile_m must be 2 or 4");
         c->tile_m = (int)value;
-        c->warps = (value == 4) ? 8 : 11;
+        c->warps = (value == 4) ? 8 : 12;
+        c->realloc = (value == 2);
     } else if (k == "warps") {
         // register files are allocated in 4-warp granules: with the producer warp, 11 and 15 consumers are "free"
         if (value != 8 && value != 11 && value != 12 && value != 15) return fail(c, SR_ERR_ARG, "warps must be 8, 11, 12 or 15");
         if (c->tile_m == 4 && value != 8) return fail(c, SR_ERR_ARG, "tile_m 4 supports 8 warps only");
         c->warps = (int)value;
+        c->realloc = false;
+    } else if (k == "realloc") {
+        // dedicated producer warp living on re-allocated registers (setmaxnreg): 12 consumers x tile_m 2, or 8 x tile_m 4
+        c->realloc = value != 0;
+        if (c->realloc) c->warps = (c->tile_m == 4) ? 8 : 12;
     } else if (k == "chunk_cols") {
         if (value < 256) return fail(c, SR_ERR_ARG, "chunk_cols must be >= 256");
         c->chunk_cols = (value + 255) / 256 * 256;
     } else if (k == "holes") {
-        if (value < 0 || value > 44) return fail(c, SR_ERR_ARG, "holes must be 0, 1, 2 or a two-digit k-step pair");
+        if (value < 0 || value > 1234) return fail(c, SR_ERR_ARG, "holes must be 0, 1, 2 or the digits of the k-steps (1..4) to pause before");
         c->holes = (int)value;
     } else if (k == "compress_patterns") {
         c->compress = value != 0;
         c->last_unique = c->last_total = 0;
+    } else if (k == "input_chars") {
+        c->input_chars = value != 0;                  // applies to the next sr_set_alignment / sr_run_streamed
     } else if (k == "prefetch") {
         c->prefetch = value != 0;
     } else if (k == "debug") {
@@ -1008,5 +1036,15 @@ int sr_debug_pmatrix(sr_ctx* c, int32_t node, int32_t k, double* out) {
     }
     return SR_OK;
 }
+
+#ifdef SR_TIMELINE
+// tools/timeline.py only (not part of the ABI): clock stamps of the last prune launch, [16 warps][SR_TL_STEPS][8]
+int sr_debug_timeline(sr_ctx* c, unsigned* out, int64_t n_words) {
+    if (!c || !out || !c->d_timeline.p) return SR_ERR_ARG;
+    CUDA_TRY(c, cudaDeviceSynchronize());
+    CUDA_TRY(c, cudaMemcpy(out, c->d_timeline.p, sizeof(unsigned) * std::min<int64_t>(n_words, 16 * SR_TL_STEPS * 8), cudaMemcpyDeviceToHost));
+    return SR_OK;
+}
+#endif
 
 }  // extern "C"

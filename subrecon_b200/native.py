@@ -13,7 +13,8 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libsubrecon_b200.so")
+# SUBRECON_B200_LIB: an instrumented build of the same sources (tools/timeline.py); never a different implementation
+LIB_PATH = os.environ.get("SUBRECON_B200_LIB") or os.path.join(_PKG, "libsubrecon_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -183,6 +183,17 @@ def encode_alignment(seqs) -> np.ndarray:
     return out
 
 
+def alignment_chars(seqs) -> np.ndarray:
+    """chars -> uint8 letters[taxon][site] for the library's "input_chars" mode: the same right-padding with '-' as
+    `encode_alignment`, but the translation to states is left to the device (one pass over the uploaded bytes)."""
+    length = max((len(s) for s in seqs), default=0)
+    out = np.full((len(seqs), length), ord("-"), dtype=np.uint8)
+    for i, s in enumerate(seqs):
+        if s:
+            out[i, :len(s)] = np.frombuffer(s.encode("latin-1", "replace"), dtype=np.uint8)
+    return out
+
+
 @dataclass
 class FlatTree:
     n_nodes: int

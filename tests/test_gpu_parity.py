@@ -182,8 +182,10 @@ def test_cfg5_subset(ctx):
     check(ctx, p, lnl, joint)
 
 
-@pytest.mark.parametrize("opts", [dict(tile_m=4), dict(warps=8), dict(warps=15), dict(warps=8, rotate=0), dict(holes=0), dict(holes=1),
-                                  dict(rotate=0), dict(holes=0, rotate=0), dict(prefetch=1), dict(prefetch=1, rotate=0), dict(warps=12), dict(warps=12, rotate=0)])
+@pytest.mark.parametrize("opts", [dict(tile_m=4), dict(tile_m=4, realloc=1), dict(tile_m=4, realloc=1, rotate=0), dict(warps=8), dict(warps=15),
+                                  dict(warps=8, rotate=0), dict(holes=0), dict(holes=1), dict(holes=13), dict(holes=1234), dict(rotate=0),
+                                  dict(warps=11), dict(warps=11, rotate=0), dict(warps=11, holes=0), dict(warps=11, holes=0, rotate=0),
+                                  dict(warps=11, prefetch=1), dict(warps=11, prefetch=1, rotate=0), dict(warps=12), dict(warps=12, rotate=0)])
 def test_kernel_variants_agree(ctx, opts):
     """Every tuning variant of the pruning kernel (sr_set_option) gives oracle-exact results."""
     p = synthetic(3, 512)
@@ -195,7 +197,7 @@ def test_kernel_variants_agree(ctx, opts):
         r = ctx.run()
         assert rel_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
     finally:
-        for k, v in dict(tile_m=2, warps=11, holes=2, rotate=1, prefetch=0).items():
+        for k, v in dict(tile_m=2, holes=2, rotate=1, prefetch=0).items():      # tile_m=2 restores the default warp layout
             ctx.set_option(k, v)
 
 
@@ -236,6 +238,38 @@ def test_ragged_offsets_and_chunks(ctx, example_problem):
         assert np.array_equal(tapered[k], uniform[k])
         assert np.array_equal(tapered[k][:1170], one[k]) and np.array_equal(tapered[k][-131:], tapered[k][:131])
     assert tapered["compact"].tobytes() == uniform["compact"].tobytes()
+
+
+def test_residue_letters_encoded_on_device(ctx, example_problem):
+    """with "input_chars" the library takes the alignment's letters and applies PAL's char -> state map
+    (App. B.6) on the device. Same bits as the host-encoded path, resident and streamed, for every possible byte."""
+    p = example_problem
+    names, seqs = treeio.read_fasta(os.path.join(HERE, "golden", "example", "prot.fasta"))
+    letters = treeio.alignment_chars(seqs)
+    assert np.array_equal(treeio.encode_alignment(seqs), p.states)
+    setup(ctx, p)
+    ref = ctx.run()
+    # every byte value, both cases, gaps and ambiguity codes: 256 extra columns cycling through 0..255 on each row
+    rng = np.random.default_rng(11)
+    junk = np.stack([rng.permutation(256).astype(np.uint8) for _ in range(letters.shape[0])])
+    lower = np.frombuffer(b"".join(s.lower().encode("latin-1") for s in seqs), dtype=np.uint8).reshape(letters.shape)
+    wide = np.concatenate([letters, junk, lower], axis=1)
+    lut = treeio._STATE_LUT
+    ctx.set_alignment(lut[wide])
+    want = ctx.run()
+    try:
+        ctx.set_option("input_chars", 1)
+        ctx.set_alignment(wide)
+        got = ctx.run()
+        st = ctx.run_streamed(wide)
+        part = ctx.run_streamed(wide, site0=100, n=300)
+    finally:
+        ctx.set_option("input_chars", 0)
+    for k in ("lnl", "joint"):
+        assert np.array_equal(got[k], want[k]) and np.array_equal(st[k], want[k]) and np.array_equal(part[k], want[k][100:400])
+        assert np.array_equal(got[k][:130], ref[k]) and np.array_equal(got[k][-130:], ref[k])
+    lnl, _ = oracle.run(p.flat, np.ascontiguousarray(lut[wide]), p.model, p.rates)
+    assert lnl_err(got["lnl"], lnl) < TOL             # (junk columns can be all-missing: lnL ~ 0)
 
 
 def test_column_pattern_compression(ctx, example_problem):

@@ -36,6 +36,11 @@ def test_state_encoding():
     assert s[0].tolist() == list(range(20)) and s[1].tolist() == list(range(20))
     assert (s[2, :13] == treeio.MISSING).all()
     assert s[3, :2].tolist() == [0, 4] and (s[3, 2:] == treeio.MISSING).all()       # padded with '-' to the longest
+    # the letters form handed to the library's "input_chars" mode: same padding, translation left to the device
+    seqs = ["ARNDCQEGHILKMFPSTWYV", "arndcqeghilkmfpstwyv", "-_?.*XBJZOU1 ", "AC"]
+    letters = treeio.alignment_chars(seqs)
+    assert letters.shape == s.shape and bytes(letters[3]) == b"AC" + b"-" * 18
+    assert np.array_equal(treeio._STATE_LUT[letters], s)
 
 
 def test_flatten_unknown_taxon():

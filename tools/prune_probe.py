@@ -23,12 +23,15 @@ ap.add_argument("--taxa", type=int, default=1000)
 ap.add_argument("--tree", default="yule")
 ap.add_argument("--ncat", type=int, default=4)
 ap.add_argument("--uniform", action="store_true", help="uniform random states instead of simulated columns")
+ap.add_argument("--const", action="store_true", help="every tip in state 0 (no shared-memory bank conflicts in the tip gathers)")
 a = ap.parse_args()
 
 tree = {"yule": synth.yule_tree, "balanced": synth.balanced_tree, "caterpillar": synth.caterpillar_tree}[a.tree](a.taxa, seed=3)
 model = palmodel.host_model("wag")
 rates = palmodel.gamma_rates(a.ncat, 0.5)
-if a.uniform:
+if a.const:
+    base = np.zeros((a.taxa, 4096), dtype=np.uint8)
+elif a.uniform:
     base = np.random.default_rng(1).integers(0, 20, size=(a.taxa, 4096), dtype=np.uint8)
 else:
     base = synth.simulate_alignment(tree, model, rates, 4096, seed=103)
@@ -43,7 +46,9 @@ if a.prefetch >= 0:
     ctx.set_option("prefetch", a.prefetch)
 if a.rotate >= 0:
     ctx.set_option("rotate", a.rotate)
-if a.warps:
+if a.warps == 13:
+    ctx.set_option("realloc", 1)
+elif a.warps:
     ctx.set_option("warps", a.warps)
 ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
 ctx.set_rates(rates)
