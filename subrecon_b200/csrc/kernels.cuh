@@ -868,11 +868,24 @@ struct CompactRec {            // must match sr_compact in include/subrecon_b200
 
 // one warp per column; lane a < 20 owns row a of the 20x20 joint matrix
 constexpr int ROOT_WARPS = 8;
+// SMEMP: the K merged root-branch matrices are staged once per CTA in dynamic shared memory, transposed ([k][b][a]) so
+// that lane a's 20 reads per rate class are conflict-free; read straight from global memory they are 20 strided
+// 8-byte loads per lane and rate class, and the L1 sector traffic of those was what bounded this kernel.
+constexpr int ROOT_SMEM_MAX_K = 16;
+template <bool SMEMP>
 __global__ void __launch_bounds__(ROOT_WARPS * 32) root_kernel(RootParams p) {
     __shared__ double sB[ROOT_WARPS][NS];
     __shared__ double sOut[ROOT_WARPS][NS * NS];
+    extern __shared__ __align__(16) double sP[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double LN2 = 0.693147180559945309417232121458;
+    if (SMEMP) {
+        for (int e = threadIdx.x; e < p.K * NS * NS; e += blockDim.x) {
+            const int k = e / (NS * NS), ab = e - k * (NS * NS), a = ab / NS, b = ab - a * NS;
+            sP[k * (NS * NS) + b * NS + a] = p.proot[e];
+        }
+        __syncthreads();
+    }
     for (int64_t oc = (int64_t)blockIdx.x * ROOT_WARPS + warp; oc < p.n; oc += (int64_t)gridDim.x * ROOT_WARPS) {
         const int64_t col = oc + p.col_skip;
         int emax = INT_MIN;
@@ -891,9 +904,15 @@ __global__ void __launch_bounds__(ROOT_WARPS * 32) root_kernel(RootParams p) {
             __syncwarp();
             if (lane < NS) {
                 const double fa = wk * (pia * pa[lane]);
-                const double* pr = p.proot + (size_t)k * NS * NS + lane * NS;
+                if (SMEMP) {
+                    const double* pr = sP + k * (NS * NS) + lane;
 #pragma unroll
-                for (int b = 0; b < NS; ++b) row[b] = fma(fa * pr[b], sB[warp][b], row[b]);
+                    for (int b = 0; b < NS; ++b) row[b] = fma(fa * pr[b * NS], sB[warp][b], row[b]);
+                } else {
+                    const double* pr = p.proot + (size_t)k * NS * NS + lane * NS;
+#pragma unroll
+                    for (int b = 0; b < NS; ++b) row[b] = fma(fa * pr[b], sB[warp][b], row[b]);
+                }
             }
         }
         double rs = 0.0;

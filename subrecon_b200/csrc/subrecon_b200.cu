@@ -451,7 +451,13 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     r.K = c->K;
     const int64_t blocks = std::min<int64_t>((n + ROOT_WARPS - 1) / ROOT_WARPS, (int64_t)c->n_sm * 8);
     prof_begin(c, s, 2, n);
-    root_kernel<<<(unsigned)blocks, ROOT_WARPS * 32, 0, s>>>(r);
+    if (c->K <= ROOT_SMEM_MAX_K) {
+        const int psm = c->K * NS * NS * (int)sizeof(double);
+        CUDA_TRY(c, cudaFuncSetAttribute(root_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+        root_kernel<true><<<(unsigned)blocks, ROOT_WARPS * 32, psm, s>>>(r);
+    } else {
+        root_kernel<false><<<(unsigned)blocks, ROOT_WARPS * 32, 0, s>>>(r);
+    }
     prof_end(c, s);
     CUDA_TRY(c, cudaGetLastError());
     return SR_OK;
