@@ -321,7 +321,9 @@ def test_polytomy_missing_data_custom_rates(ctx):
     flat = treeio.flatten_tree(tree)
     model = oracle.OracleModel("BLOSUM62")
     states = treeio.encode_alignment(["AV-W", "AV-W", "L--C", "LI-C", "KI-Y", "K?-y", "xV-W", "AB-W"])
-    for rates in (np.array([1.0]), np.array([0.3, 1.7]), np.array([0.0, 0.5, 2.5]), oracle.gamma_rates(8, 0.5)):
+    # K = 16 is the most the root kernel stages in shared memory, K = 20 takes its global-memory variant
+    for rates in (np.array([1.0]), np.array([0.3, 1.7]), np.array([0.0, 0.5, 2.5]), oracle.gamma_rates(8, 0.5),
+                  oracle.gamma_rates(16, 0.7), oracle.gamma_rates(20, 1.3)):
         lnl, joint = oracle.run(flat, states, model, rates)
         ctx.set_option("tile_m", 2)
         ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
