@@ -30,6 +30,8 @@ constexpr int FRAG_DOUBLES = 512;                 // a 20x20 matrix as 15 (+1 pa
 constexpr int FRAG_BYTES = FRAG_DOUBLES * 8;      // 4096
 constexpr int TABLE_DOUBLES = 21 * NS;            // P^T rows for states 0..19 + the missing-data row
 constexpr int TABLE_BYTES = TABLE_DOUBLES * 8;    // 3360
+constexpr int CHERRY_ROWS = 21 * 21;          // state pairs (s_a, s_b), 20 = missing
+constexpr int CHERRY_ROW_DOUBLES = 24;        // 4 groups of 5 values + 1 pad: a lane fetches its group with three 16-byte loads
 
 // ------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -165,6 +167,75 @@ __global__ void __launch_bounds__(128) pbuild_kernel(PBuildParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------- K1b
+// Cherry tables (see build_schedule): for a collapsed cherry v = (a, b) and every state pair (s_a, s_b) in 0..20 (20 =
+// missing data), the vector v hands to its parent, in the reference's own order of operations
+// (JointBranchReconstruction.java:208-230): partial_v[k] = P_a[k][s_a] * P_b[k][s_b] (a missing tip contributes the row
+// sum of its matrix), then sum_i = sum over k ascending of P_v[i][k] * partial_v[k], separate multiply and add.
+// Row layout: 4 groups of {5 values, 1 pad} so that the lane owning states 5q..5q+4 fetches its group with three
+// 16-byte loads. grid (n_cherry, K), block 256.
+struct CherryParams {
+    const double* eval;        // [20]
+    const double* evec;        // [400]
+    const double* ievc;        // [400]
+    const double* rates;       // [K]
+    const double* blen;        // [n_cherry][3] = {tip a, tip b, v}
+    double* ctab;              // [K][n_cherry][CHERRY_ROWS][CHERRY_ROW_DOUBLES]
+    int64_t rate_stride;
+    int n_cherry;
+};
+
+__global__ void __launch_bounds__(256) cherry_kernel(CherryParams p) {
+    __shared__ double iexp[NS * NS];
+    __shared__ double Pm[3][NS * NS];
+    __shared__ double Tt[2][21 * NS];                  // Tt[m][s][k] = P_m[k][s]; s = 20: row sum of P_m
+    const int cid = blockIdx.x, kr = blockIdx.y, tid = threadIdx.x;
+    const double rate = p.rates[kr];
+    for (int m = 0; m < 3; ++m) {
+        double t = p.blen[cid * 3 + m] * rate;
+        if (t < 1e-9) t = 1e-9;
+        __syncthreads();
+        for (int e = tid; e < NS * NS; e += 256) iexp[e] = __dmul_rn(p.ievc[e], exp(__dmul_rn(t, p.eval[e / NS])));
+        __syncthreads();
+        for (int e = tid; e < NS * NS; e += 256) {
+            const int i = e / NS, j = e % NS;
+            double s = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < NS; ++kk) s = __dadd_rn(s, __dmul_rn(p.evec[i * NS + kk], iexp[kk * NS + j]));
+            Pm[m][e] = fabs(s);
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < 2 * 21 * NS; e += 256) {
+        const int m = e / (21 * NS), sk = e % (21 * NS), st = sk / NS, k = sk % NS;
+        double v;
+        if (st < NS) v = Pm[m][k * NS + st];
+        else {
+            double acc = 0.0;
+            for (int j = 0; j < NS; ++j) acc = __dadd_rn(acc, Pm[m][k * NS + j]);
+            v = acc;
+        }
+        Tt[m][sk] = v;
+    }
+    __syncthreads();
+    double* out = p.ctab + (size_t)kr * p.rate_stride + (size_t)cid * CHERRY_ROWS * CHERRY_ROW_DOUBLES;
+    for (int e = tid; e < CHERRY_ROWS * CHERRY_ROW_DOUBLES; e += 256) {
+        const int row = e / CHERRY_ROW_DOUBLES, col = e % CHERRY_ROW_DOUBLES, grp = col / 6, r = col % 6;
+        double v = 0.0;
+        if (r < 5) {
+            const int i = grp * 5 + r, sa = row / 21, sb = row % 21;
+            const double* ta = Tt[0] + sa * NS;
+            const double* tb = Tt[1] + sb * NS;
+            const double* pv = Pm[2] + i * NS;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) s = __dadd_rn(s, __dmul_rn(pv[k], __dmul_rn(ta[k], tb[k])));
+            v = s;
+        }
+        out[e] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- K0
 // In-place clamp of the uploaded state codes to 0..20 (20 = missing data: any code outside 0..19,
 // JointBranchReconstruction.java:199-205), so the pruning kernel can index its 21-row gather tables directly.
@@ -285,11 +356,16 @@ enum : int32_t {
     STF_PUSH = 1 << 7,
     STF_STORE_A = 1 << 8,
     STF_STORE_B = 1 << 9,
-    STF_ANY = STF_RESCALE | STF_PUSH | STF_STORE_A | STF_STORE_B
+    STF_ANY = STF_RESCALE | STF_PUSH | STF_STORE_A | STF_STORE_B,
+    ST_PSEUDO_SHIFT = 10,    // bits 10-11: 1-based position (among the step's gathers) of its cherry-table gather, 0 = none
+    ST_CHERRY_SHIFT = 13     // bits 13-31: index of that cherry's table
 };
+constexpr int STEP_INTS = 8;                  // {word, row of gather 0, 1, 2}, {second row of the cherry gather, 0, 0, 0}
 
 struct PruneParams {
-    const int4* steps;         // [n_steps] {word, row of leaf 0, 1, 2}
+    const int4* steps;         // [n_steps][2] {word, row of gather 0, 1, 2}, {second row of the cherry gather, -, -, -}
+    const double* ctab;        // [K][n_cherry][CHERRY_ROWS][CHERRY_ROW_DOUBLES] cherry tables
+    int64_t ctab_rate_stride;  // doubles per rate class
     const int32_t* step_off;   // [n_steps] offset (doubles) of the step's matrices inside one rate class's stream
     const double* pstream;     // [K][rate_stride]
     const uint8_t* states;     // device alignment block, states[row*pitch + col]
@@ -324,7 +400,7 @@ struct PruneCfg {
     static constexpr int LEVEL_DOUBLES = W * M * 5 * 32;
     static constexpr int LEVEL_BYTES = LEVEL_DOUBLES * 8;
     static constexpr int STATES_OFF = FRAG_BYTES + 3 * TABLE_BYTES;                 // 13920
-    static constexpr int STAGE_BYTES = ((STATES_OFF + 3 * S + 127) / 128) * 128;
+    static constexpr int STAGE_BYTES = ((STATES_OFF + 4 * S + 127) / 128) * 128;    // 3 gather rows + the cherry gather's second row
 };
 
 __host__ __device__ constexpr int prune_bar_bytes(int nstage) { return ((2 * nstage * 8 + 127) / 128) * 128; }
@@ -393,18 +469,20 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
     uint32_t it = 0;                                  // ring position, runs on across work items
 
     // issue the TMA copies of one step (global ring position itp; work item `item_p`, step `step_p`) — one thread
-    auto issue_step = [&](uint32_t itp, int item_p, const int4 d, const int off_d, bool wait_empty) {
+    auto issue_step = [&](uint32_t itp, int item_p, const int4 d, const int row_b, const int off_d, bool wait_empty) {
         const int kp = item_p / p.n_tiles, tilep = item_p - kp * p.n_tiles;
         const double* ps = p.pstream + (size_t)kp * p.rate_stride;
         const uint8_t* st = p.states + p.col0 + (int64_t)tilep * S;
         const int stage = itp % NSTAGE;
         const uint32_t ph = (itp / NSTAGE) & 1;
         const int n_leaf = ((d.x >> ST_NPRE_SHIFT) & 3) + ((d.x & ST_NPOST) ? 1 : 0);
-        const uint32_t pbytes = ((d.x & ST_MV_MASK) ? FRAG_BYTES : 0) + n_leaf * TABLE_BYTES;
+        const int pseudo = ((d.x >> ST_PSEUDO_SHIFT) & 3) ? 1 : 0;          // a cherry gather brings a second state row, no table
+        const uint32_t pbytes = ((d.x & ST_MV_MASK) ? FRAG_BYTES : 0) + (n_leaf - pseudo) * TABLE_BYTES;
         if (wait_empty) mbar_wait(&empty[stage], ph ^ 1);
         unsigned char* dst = stages + stage * STAGE_BYTES;
-        mbar_expect_tx(&full[stage], pbytes + n_leaf * S);
-        bulk_g2s(dst, ps + off_d, pbytes, &full[stage]);
+        mbar_expect_tx(&full[stage], pbytes + (n_leaf + pseudo) * S);
+        if (pseudo) bulk_g2s(dst + Cfg::STATES_OFF + 3 * S, st + (int64_t)row_b * p.pitch, S, &full[stage]);
+        if (pbytes) bulk_g2s(dst, ps + off_d, pbytes, &full[stage]);
         if (n_leaf > 0) bulk_g2s(dst + Cfg::STATES_OFF, st + (int64_t)d.y * p.pitch, S, &full[stage]);
         if (n_leaf > 1) bulk_g2s(dst + Cfg::STATES_OFF + S, st + (int64_t)d.z * p.pitch, S, &full[stage]);
         if (n_leaf > 2) bulk_g2s(dst + Cfg::STATES_OFF + 2 * S, st + (int64_t)d.w * p.pitch, S, &full[stage]);
@@ -414,7 +492,8 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
     auto produce = [&]() {
         if (lane == 0) {
             for (int item = blockIdx.x; item < n_items; item += gridDim.x)
-                for (int step = 0; step < p.n_steps; ++step, ++it) issue_step(it, item, __ldg(p.steps + step), __ldg(p.step_off + step), true);
+                for (int step = 0; step < p.n_steps; ++step, ++it)
+                    issue_step(it, item, __ldg(p.steps + 2 * step), __ldg(&p.steps[2 * step + 1].x), __ldg(p.step_off + step), true);
         }
     };
     if (RA) {
@@ -447,10 +526,10 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
     uint32_t my_pos = (uint32_t)warp;
     int my_item = blockIdx.x, my_step = warp;
     int4 my_d = make_int4(0, 0, 0, 0);
-    int my_off = 0;
+    int my_off = 0, my_rowb = 0;
     auto my_normalise = [&]() {
         while (my_item < n_items && my_step >= p.n_steps) { my_step -= p.n_steps; my_item += gridDim.x; }
-        if (my_item < n_items) { my_d = __ldg(p.steps + my_step); my_off = __ldg(p.step_off + my_step); }
+        if (my_item < n_items) { my_d = __ldg(p.steps + 2 * my_step); my_rowb = __ldg(&p.steps[2 * my_step + 1].x); my_off = __ldg(p.step_off + my_step); }
     };
     // try (or, if `block`, wait) to refill my next position; returns after at most one refill
     auto my_refill = [&](bool block) {
@@ -463,7 +542,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
         bool ok = mbar_test_wait(&empty[stg_], par_);
         if (!ok && block) { mbar_wait(&empty[stg_], par_); ok = true; }
         if (!ok) return;
-        if (lane == 0) issue_step(my_pos, my_item, my_d, my_off, false);
+        if (lane == 0) issue_step(my_pos, my_item, my_d, my_rowb, my_off, false);
         __syncwarp();
         my_pos += W;
         my_step += W;
@@ -479,6 +558,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int k = item / p.n_tiles, tile = item - k * p.n_tiles;
+        const double* ctab_k = p.ctab + (size_t)k * p.ctab_rate_stride + q * 6;
         double A[M][5];
         int cnt[M];
 #pragma unroll
@@ -512,7 +592,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
             const uint32_t ph = (it / NSTAGE) & 1;
             const int w = w_next;
             const bool has_next = step + 1 < p.n_steps;
-            if (has_next) w_next = __ldg(&p.steps[step + 1].x);
+            if (has_next) w_next = __ldg(&p.steps[2 * (step + 1)].x);
             SR_TL(0);                                   // step begins
             if (INL) my_refill(/*block=*/my_pos <= it);
             const int mv = w & ST_MV_MASK, n_pre = (w >> ST_NPRE_SHIFT) & 3;
@@ -564,39 +644,53 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
                 }
             }
             // ---- tips below this node (gathers of P^T rows by observed state): loads first ...
+            // At most one of the step's gathers is a collapsed cherry (position ps, 1-based): its row, selected by the state
+            // PAIR of the cherry's two tips, comes from the cherry's table in global memory (L2) instead of the stage.
+            const int ps = (w >> ST_PSEUDO_SHIFT) & 3;
+            const double* crow[M];
+            if (ps) {
+                const unsigned cid = (unsigned)w >> ST_CHERRY_SHIFT;
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    const int sa = ps == 1 ? s0[j] : (ps == 2 ? s1[j] : s2[j]);
+                    const int sb = stb[3 * S + j * 8];
+                    crow[j] = ctab_k + ((size_t)cid * CHERRY_ROWS + sa * 21 + sb) * CHERRY_ROW_DOUBLES;
+                }
+            }
+            // gather number `pos` (1-based) of the step; `tix` = index of its table among the step's staged tables
+            auto gather = [&](double (&dst)[M][5], const int (&sx)[M], int pos, int tix) {
+                if (ps == pos) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) {
+                        double pad;
+                        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(dst[j][0]), "=d"(dst[j][1]) : "l"(crow[j]));
+                        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+16];" : "=d"(dst[j][2]), "=d"(dst[j][3]) : "l"(crow[j]));
+                        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+32];" : "=d"(dst[j][4]), "=d"(pad) : "l"(crow[j]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) {
+                        const double* row = tab + tix * TABLE_DOUBLES + sx[j] * NS;
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) dst[j][r] = row[r];
+                    }
+                }
+            };
             double tp0[M][5], tp1[M][5];
-            if (n_pre >= 1) {
+            if (n_pre >= 1) gather(tp0, s0, 1, 0);
+            if (n_pre == 2) gather(tp1, s1, 2, ps == 1 ? 0 : 1);
+            int spost[M];
 #pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    const double* row = tab + s0[j] * NS;
-#pragma unroll
-                    for (int r = 0; r < 5; ++r) tp0[j][r] = row[r];
-                }
-            }
-            if (n_pre == 2) {
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    const double* row = tab + TABLE_DOUBLES + s1[j] * NS;
-#pragma unroll
-                    for (int r = 0; r < 5; ++r) tp1[j][r] = row[r];
-                }
-            }
+            for (int j = 0; j < M; ++j) spost[j] = n_pre == 0 ? s0[j] : (n_pre == 1 ? s1[j] : s2[j]);
+            const int post_tix = n_pre - ((ps && ps <= n_pre) ? 1 : 0);
             double vp[M][5];
-            if (mv && (w & ST_NPOST) && !LAZY) {
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    const int sx = n_pre == 0 ? s0[j] : (n_pre == 1 ? s1[j] : s2[j]);
-                    const double* row = tab + n_pre * TABLE_DOUBLES + sx * NS;
-#pragma unroll
-                    for (int r = 0; r < 5; ++r) vp[j][r] = row[r];
-                }
-            }
+            if (mv && (w & ST_NPOST) && !LAZY) gather(vp, spost, n_pre + 1, post_tix);
             // The post-MMA operands are only consumed after the burst. Pin them here so the compiler cannot sink their loads
             // below the burst (it may move plain loads across the volatile DMMAs): the stage is released right after the
             // burst, and a load from it that is still in flight then races the TMA refill (seen as 1-in-10 runs with a few
             // columns off by 1e-5 at 5,000 taxa; tests/test_gpu_parity.py::*full_size*, tools/stress_big.py).
             if (!LAZY && mv) {
-                if (w & ST_NPOST) {
+                if ((w & ST_NPOST) && ps != n_pre + 1) {       // (a cherry row comes from global memory: it may stay in flight)
 #pragma unroll
                     for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -695,15 +789,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
                     next_ready = (p.debug & 2) ? false : mbar_test_wait(&full[itp % NSTAGE], (itp / NSTAGE) & 1);
                 }
                 if (LAZY) {
-                    if (w & ST_NPOST) {
-#pragma unroll
-                        for (int j = 0; j < M; ++j) {
-                            const int sx = n_pre == 0 ? s0[j] : (n_pre == 1 ? s1[j] : s2[j]);
-                            const double* row = tab + n_pre * TABLE_DOUBLES + sx * NS;
-#pragma unroll
-                            for (int r = 0; r < 5; ++r) vp[j][r] = row[r];
-                        }
-                    }
+                    if (w & ST_NPOST) gather(vp, spost, n_pre + 1, post_tix);
                     if (mv == 2) {
                         if (sp < p.smem_levels) {
                             const double* src = my_stack + (size_t)sp * (W * TILE_DOUBLES);

@@ -68,6 +68,10 @@ struct sr_ctx {
     int32_t max_leaf_row = -1;
     double root_blen = 0.0;
     bool sched_dirty = true, p_dirty = true;
+    // collapsed cherries (an internal node whose two children are tips, not a root child): node, tip rows, edge lengths
+    std::vector<int32_t> cherry_node;
+    std::vector<double> cherry_blen;             // [n_cherry][3] = {tip a, tip b, the node's own edge}
+    DevBuf d_ctab, d_cherry_blen;
 #ifdef SR_TIMELINE
     DevBuf d_timeline;
 #endif
@@ -76,6 +80,8 @@ struct sr_ctx {
     int tile_m = 2;
     int debug = 0;
     int holes = 2;                      // pauses inside a warp's MMA burst (0..2), see kernels.cuh
+    int cherry_tables = 1;              // collapse cherries into 441-row lookup tables (see build_schedule)
+    int64_t cherry_table_mb = 1024;     // memory cap for those tables; cherries beyond it are pruned the ordinary way
     bool input_chars = false;           // alignment bytes are residue letters, translated on the device
     int compress = 0;                   // reduce every batch to its distinct column patterns first
     int prefetch = 0;                   // fetch the next step's first operands inside the current MMA burst
@@ -153,13 +159,33 @@ int build_schedule(sr_ctx* c) {
         }
     }
     if ((int)order.size() != n) return fail(c, SR_ERR_ARG, "tree is not connected: %d of %d nodes reachable from the root", (int)order.size(), n);
+    // Cherry tables. For an internal node v with exactly two tip children a, b (and v not a root child), the vector v hands
+    // to its parent, u[i] = sum_k P_v[i][k] * P_a[k][s_a] * P_b[k][s_b], depends on the column only through the state pair
+    // (s_a, s_b): 21 x 21 possibilities. K1 tabulates u for all of them once per rate class (CHERRY_ROWS x 20 doubles), and
+    // the pruning kernel treats v as a tip with 441 states: two gathers and one 20x20 contraction per column become one
+    // gather. A Yule tree has ~N/3 cherries, a balanced one N/2, so a third to a half of all contractions disappear.
+    std::vector<int32_t> cherry_of(n, -1);
+    c->cherry_node.clear(); c->cherry_blen.clear();
+    if (c->cherry_tables && !c->prefetch) {
+        const int64_t per = (int64_t)std::max(1, c->K) * CHERRY_ROWS * CHERRY_ROW_DOUBLES * (int64_t)sizeof(double);
+        const int64_t cap = std::min<int64_t>((c->cherry_table_mb << 20) / per, (1 << 19) - 1);
+        for (int v = 0; v < n && (int64_t)c->cherry_node.size() < cap; ++v) {
+            if (v == c->root || v == rc0 || v == rc1 || off[v + 1] - off[v] != 2) continue;
+            const int a = idx[off[v]], b = idx[off[v] + 1];
+            if (!is_leaf(a) || !is_leaf(b)) continue;
+            cherry_of[v] = (int32_t)c->cherry_node.size();
+            c->cherry_node.push_back(v);
+            c->cherry_blen.push_back(c->blen[a]); c->cherry_blen.push_back(c->blen[b]); c->cherry_blen.push_back(c->blen[v]);
+        }
+    }
+    auto is_tip = [&](int v) { return is_leaf(v) || cherry_of[v] >= 0; };
     std::vector<int> need(n, 0);
     std::vector<int32_t> ord(idx.size());      // per node: children reordered (internal by need desc, then tips)
     for (int oi = n - 1; oi >= 0; --oi) {
         const int v = order[oi];
-        if (is_leaf(v)) continue;
+        if (is_tip(v)) continue;
         std::vector<int> inner, tips;
-        for (int e = off[v]; e < off[v + 1]; ++e) (is_leaf(idx[e]) ? tips : inner).push_back(idx[e]);
+        for (int e = off[v]; e < off[v + 1]; ++e) (is_tip(idx[e]) ? tips : inner).push_back(idx[e]);
         std::stable_sort(inner.begin(), inner.end(), [&](int a, int b) { return need[a] > need[b]; });
         int nd = 0;
         for (size_t i = 0; i < inner.size(); ++i) nd = std::max(nd, need[inner[i]] + (i > 0 ? 1 : 0));
@@ -193,7 +219,7 @@ int build_schedule(sr_ctx* c) {
                     continue;
                 }
                 const int ch = ord[off[v] + f.i];
-                if (!is_leaf(ch)) {
+                if (!is_tip(ch)) {
                     if (f.i > 0) prims.back().push = true;        // keep the partial while the sibling subtree runs
                     ++f.i;
                     fr.push_back({ch, 0});
@@ -217,6 +243,13 @@ int build_schedule(sr_ctx* c) {
     std::vector<int> s_stack;
     int64_t off_d = 0;
     auto add_slot = [&](const Prim& pr) {
+        if (cherry_of[pr.child] >= 0) {          // no matrices in the stream: the table lives in its own buffer
+            const int a = idx[off[pr.child]], b = idx[off[pr.child] + 1];
+            c->node_slot[pr.child] = -2 - cherry_of[pr.child];
+            c->e_leaf += 2; ++c->e_int;          // the algorithmic work it stands for is unchanged
+            c->max_leaf_row = std::max(c->max_leaf_row, std::max(c->leaf_row[a], c->leaf_row[b]));
+            return;
+        }
         const bool leaf = pr.code <= P_LEAF_MUL;
         c->slot_kind.push_back(pr.identity ? SLOT_IDENTITY : (leaf ? SLOT_TABLE : SLOT_FRAG));
         c->slot_off.push_back((int32_t)off_d);
@@ -228,14 +261,31 @@ int build_schedule(sr_ctx* c) {
     };
     size_t i = 0;
     while (i < prims.size()) {
-        int32_t word = 0, rows[3] = {0, 0, 0};
+        int32_t word = 0, rows[3] = {0, 0, 0}, row_b = 0;
         int n_leaf = 0, n_pre = 0;
+        int pseudo_at = 0;                       // 1-based gather position of the step's cherry-table gather (at most one)
+        auto is_pseudo = [&](const Prim& pr) { return pr.code <= P_LEAF_MUL && cherry_of[pr.child] >= 0; };
+        auto take_gather = [&](const Prim& pr) {
+            if (is_pseudo(pr)) {
+                const int a = idx[off[pr.child]], b = idx[off[pr.child] + 1];
+                rows[n_leaf++] = c->leaf_row[a];
+                row_b = c->leaf_row[b];
+                pseudo_at = n_leaf;
+                word |= (pseudo_at << ST_PSEUDO_SHIFT) | (cherry_of[pr.child] << ST_CHERRY_SHIFT);
+                ++s_cur;                         // two edges deep
+            } else {
+                rows[n_leaf++] = c->leaf_row[pr.child];
+            }
+        };
         bool ended = false;                      // a push/store flag closes the step
         const size_t first = i;
         // the step's matrices are laid out [MV fragments][tables...] — find the MV (if any) first
         size_t j = i;
         int pre = 0;
-        while (j < prims.size() && prims[j].code <= P_LEAF_MUL && pre < 2 && !(j > i && prims[j].code == P_LEAF_SET)) {
+        bool seen_pseudo = false;
+        while (j < prims.size() && prims[j].code <= P_LEAF_MUL && pre < 2 && !(j > i && prims[j].code == P_LEAF_SET) &&
+               !(seen_pseudo && is_pseudo(prims[j]))) {
+            seen_pseudo = seen_pseudo || is_pseudo(prims[j]);
             ++pre; ++j;
             if (prims[j - 1].push || prims[j - 1].store_a || prims[j - 1].store_b) { ended = true; break; }
         }
@@ -247,7 +297,7 @@ int build_schedule(sr_ctx* c) {
             const Prim& pr = prims[t];
             if (t == first && pr.code == P_LEAF_SET) { word |= ST_PRE0_SET; s_cur = 0; }
             add_slot(pr);
-            rows[n_leaf++] = c->leaf_row[pr.child];
+            take_gather(pr);
             ++n_pre; ++s_cur;
         }
         i += pre;
@@ -260,10 +310,10 @@ int build_schedule(sr_ctx* c) {
             last = &pr;
             i = mv_at + 1;
             ended = pr.push || pr.store_a || pr.store_b;
-            if (!ended && i < prims.size() && prims[i].code == P_LEAF_MUL) {
+            if (!ended && i < prims.size() && prims[i].code == P_LEAF_MUL && !(pseudo_at && is_pseudo(prims[i]))) {
                 const Prim& pl = prims[i];
                 add_slot(pl);
-                rows[n_leaf++] = c->leaf_row[pl.child];
+                take_gather(pl);
                 word |= ST_NPOST;
                 ++s_cur;
                 last = &pl;
@@ -277,6 +327,7 @@ int build_schedule(sr_ctx* c) {
         if (last->store_b) word |= STF_STORE_B;
         c->steps.push_back(word);
         c->steps.push_back(rows[0]); c->steps.push_back(rows[1]); c->steps.push_back(rows[2]);
+        c->steps.push_back(row_b); c->steps.push_back(0); c->steps.push_back(0); c->steps.push_back(0);
         if (off_d > INT32_MAX - 4096) return fail(c, SR_ERR_UNSUPPORTED, "tree too large for 32-bit matrix-stream offsets");
     }
     c->rate_stride = off_d;
@@ -306,10 +357,10 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
         return fail(c, SR_ERR_STATE, "model, rates and tree must be set before running");
     if (c->sched_dirty) { int rc = build_schedule(c); if (rc) return rc; }
     if (!c->p_dirty) return SR_OK;
-    const int n_steps = (int)c->steps.size() / 4, n_slots = (int)c->slot_kind.size();
+    const int n_steps = (int)c->steps.size() / STEP_INTS, n_slots = (int)c->slot_kind.size();
     CUDA_TRY(c, c->d_model.reserve(sizeof(double) * 840));
     CUDA_TRY(c, c->d_rates.reserve(sizeof(double) * c->K));
-    CUDA_TRY(c, c->d_steps.reserve(sizeof(int32_t) * 4 * n_steps));
+    CUDA_TRY(c, c->d_steps.reserve(sizeof(int32_t) * STEP_INTS * n_steps));
     CUDA_TRY(c, c->d_stepoff.reserve(sizeof(int32_t) * n_steps));
     CUDA_TRY(c, c->d_slotkind.reserve(sizeof(int32_t) * n_slots));
     CUDA_TRY(c, c->d_slotoff.reserve(sizeof(int32_t) * n_slots));
@@ -323,7 +374,7 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     // it may return before the DMA has landed). The stream is drained before the staging arrays go out of scope.
     CUDA_TRY(c, cudaMemcpyAsync(c->d_model.p, hm, sizeof(hm), cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_rates.p, c->rates.data(), sizeof(double) * c->K, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_steps.p, c->steps.data(), sizeof(int32_t) * 4 * n_steps, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_steps.p, c->steps.data(), sizeof(int32_t) * STEP_INTS * n_steps, cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_stepoff.p, c->step_off.data(), sizeof(int32_t) * n_steps, cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_slotkind.p, c->slot_kind.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_slotoff.p, c->slot_off.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, s));
@@ -347,6 +398,22 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     pbuild_kernel<<<dim3(n_slots + 1, c->K), 128, 0, s>>>(pp);
     prof_end(c, s);
     CUDA_TRY(c, cudaGetLastError());
+    const int n_cherry = (int)c->cherry_node.size();
+    if (n_cherry > 0) {
+        const int64_t stride = (int64_t)n_cherry * CHERRY_ROWS * CHERRY_ROW_DOUBLES;
+        CUDA_TRY(c, c->d_ctab.reserve(sizeof(double) * (size_t)c->K * stride));
+        CUDA_TRY(c, c->d_cherry_blen.reserve(sizeof(double) * 3 * n_cherry));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_cherry_blen.p, c->cherry_blen.data(), sizeof(double) * 3 * n_cherry, cudaMemcpyHostToDevice, s));
+        CherryParams cp{};
+        cp.eval = pp.eval; cp.evec = pp.evec; cp.ievc = pp.ievc; cp.rates = pp.rates;
+        cp.blen = c->d_cherry_blen.as<double>();
+        cp.ctab = c->d_ctab.as<double>();
+        cp.rate_stride = stride;
+        cp.n_cherry = n_cherry;
+        cherry_kernel<<<dim3(n_cherry, c->K), 256, 0, s>>>(cp);
+        CUDA_TRY(c, cudaGetLastError());
+        CUDA_TRY(c, cudaStreamSynchronize(s));       // cherry_blen staging is host memory owned by the context; keep it simple
+    }
     c->p_dirty = false;
     return SR_OK;
 }
@@ -393,6 +460,8 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     p.steps = c->d_steps.as<int4>();
     p.step_off = c->d_stepoff.as<int32_t>();
     p.pstream = c->d_pstream.as<double>();
+    p.ctab = c->d_ctab.as<double>();
+    p.ctab_rate_stride = (int64_t)c->cherry_node.size() * CHERRY_ROWS * CHERRY_ROW_DOUBLES;
     p.rate_stride = c->rate_stride;
     p.states = d_states;
     p.pitch = pitch;
@@ -400,7 +469,7 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     p.rootpart = c->d_rootpart.as<double>();
     p.rootexp = c->d_rootexp.as<int32_t>();
     p.ncp = ncp;
-    p.n_steps = (int)c->steps.size() / 4;
+    p.n_steps = (int)c->steps.size() / STEP_INTS;
     p.n_tiles = (int)tiles;
     p.K = c->K;
     p.debug = c->debug;
@@ -606,6 +675,7 @@ int sr_set_rates(sr_ctx* c, int K, const double* rates) {
     if (!rates) return fail(c, SR_ERR_ARG, "rates is NULL");
     for (int i = 0; i < K; ++i)
         if (!std::isfinite(rates[i]) || rates[i] < 0.0) return fail(c, SR_ERR_ARG, "rate %d is not a finite non-negative number", i);
+    if (K != c->K) c->sched_dirty = true;            // the cherry-table memory cap is per rate class
     c->K = K;
     c->rates.assign(rates, rates + K);
     c->has_rates = true;
@@ -892,10 +962,18 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     } else if (k == "compress_patterns") {
         c->compress = value != 0;
         c->last_unique = c->last_total = 0;
+    } else if (k == "cherry_tables") {
+        c->cherry_tables = value != 0;
+        c->sched_dirty = true;
+    } else if (k == "cherry_table_mb") {
+        if (value < 0) return fail(c, SR_ERR_ARG, "cherry_table_mb must be >= 0");
+        c->cherry_table_mb = value;
+        c->sched_dirty = true;
     } else if (k == "input_chars") {
         c->input_chars = value != 0;                  // applies to the next sr_set_alignment / sr_run_streamed
     } else if (k == "prefetch") {
         c->prefetch = value != 0;
+        c->sched_dirty = true;                       // (the prefetching variant does not take cherry gathers)
     } else if (k == "debug") {
         c->debug = (int)value;
     } else if (k == "rotate") {
@@ -952,15 +1030,15 @@ int sr_schedule_info(sr_ctx* c, int64_t* n_steps, int32_t* stack_depth, double* 
     if (!c) return SR_ERR_ARG;
     if (!c->has_tree) return fail(c, SR_ERR_STATE, "tree not set");
     if (c->sched_dirty) { int rc = build_schedule(c); if (rc) return rc; }
-    if (n_steps) *n_steps = (int64_t)c->steps.size() / 4;
+    if (n_steps) *n_steps = (int64_t)c->steps.size() / STEP_INTS;
     if (stack_depth) *stack_depth = c->need_depth;
     if (flops) *flops = 820.0 * (double)c->e_int + 20.0 * (double)c->e_leaf + 1200.0;
     return SR_OK;
 }
 
 int sr_schedule_dump(int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
-                     const int32_t* leaf_row, int32_t root, int32_t rescale_every, int64_t cap_steps, int32_t* steps,
-                     int32_t* node_slot, int64_t* n_steps, int32_t* stack_depth) {
+                     const int32_t* leaf_row, int32_t root, int32_t rescale_every, int32_t cherry_tables, int64_t cap_steps,
+                     int32_t* steps, int32_t* node_slot, int64_t* n_steps, int32_t* stack_depth) {
     // host-only: builds the schedule exactly as sr_set_tree does, without touching a GPU
     if (n_nodes < 3 || !child_off || !child_idx || !blen || !leaf_row || !n_steps) return SR_ERR_ARG;
     if (root < 0 || root >= n_nodes || child_off[root + 1] - child_off[root] != 2) return SR_ERR_ARG;
@@ -972,9 +1050,10 @@ int sr_schedule_dump(int32_t n_nodes, const int32_t* child_off, const int32_t* c
     tmp.blen.assign(blen, blen + n_nodes);
     tmp.leaf_row.assign(leaf_row, leaf_row + n_nodes);
     tmp.rescale_every = rescale_every > 0 ? rescale_every : 8;
+    tmp.cherry_tables = cherry_tables != 0;
     int rc = build_schedule(&tmp);
     if (rc) return rc;
-    *n_steps = (int64_t)tmp.steps.size() / 4;
+    *n_steps = (int64_t)tmp.steps.size() / STEP_INTS;
     if (stack_depth) *stack_depth = tmp.need_depth;
     if (steps) {
         if (*n_steps > cap_steps) return SR_ERR_ARG;
@@ -1023,7 +1102,7 @@ int sr_debug_pmatrix(sr_ctx* c, int32_t node, int32_t k, double* out) {
         return SR_OK;
     }
     const int slot = c->node_slot[node];
-    if (slot < 0) return fail(c, SR_ERR_ARG, "node %d has no pruning step", node);
+    if (slot < 0) return fail(c, SR_ERR_ARG, "node %d has no matrix in the stream (root child of a one-tip clade, or part of a collapsed cherry: see sr_debug_cherry_table / option cherry_tables)", node);
     double buf[FRAG_DOUBLES];
     const bool frag = c->slot_kind[slot] == SLOT_FRAG;
     CUDA_TRY(c, cudaMemcpyAsync(buf, c->d_pstream.as<double>() + (size_t)k * c->rate_stride + c->slot_off[slot],
@@ -1040,6 +1119,24 @@ int sr_debug_pmatrix(sr_ctx* c, int32_t node, int32_t k, double* out) {
         for (int s = 0; s < 20; ++s)
             for (int i = 0; i < 20; ++i) out[i * 20 + s] = buf[s * 20 + i];
     }
+    return SR_OK;
+}
+
+int sr_debug_cherry_table(sr_ctx* c, int32_t node, int32_t k, double* out) {
+    if (!c || !out) return SR_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_pstream(c, c->stream);
+    if (rc) return rc;
+    if (k < 0 || k >= c->K || node < 0 || node >= c->n_nodes) return fail(c, SR_ERR_ARG, "node or rate class out of range");
+    if (c->node_slot[node] > -2) return fail(c, SR_ERR_ARG, "node %d is not a collapsed cherry", node);
+    const int cid = -2 - c->node_slot[node];
+    std::vector<double> buf((size_t)CHERRY_ROWS * CHERRY_ROW_DOUBLES);
+    const int64_t stride = (int64_t)c->cherry_node.size() * CHERRY_ROWS * CHERRY_ROW_DOUBLES;
+    CUDA_TRY(c, cudaMemcpyAsync(buf.data(), c->d_ctab.as<double>() + (size_t)k * stride + (size_t)cid * CHERRY_ROWS * CHERRY_ROW_DOUBLES,
+                                sizeof(double) * buf.size(), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int row = 0; row < CHERRY_ROWS; ++row)
+        for (int i = 0; i < 20; ++i) out[row * 20 + i] = buf[(size_t)row * CHERRY_ROW_DOUBLES + (i / 5) * 6 + i % 5];
     return SR_OK;
 }
 

@@ -25,7 +25,7 @@ _U8 = ctypes.POINTER(ctypes.c_uint8)
 EXPORTS = ["sr_create", "sr_destroy", "sr_last_error", "sr_set_model", "sr_set_rates", "sr_set_tree",
            "sr_set_alignment", "sr_run", "sr_run_device", "sr_run_streamed", "sr_host_alloc", "sr_host_free",
            "sr_set_option", "sr_get_profile", "sr_profile_reset", "sr_schedule_info", "sr_measure_fp64_peak",
-           "sr_debug_pmatrix", "sr_schedule_dump"]
+           "sr_debug_pmatrix", "sr_debug_cherry_table", "sr_schedule_dump"]
 
 
 class SrError(RuntimeError):
@@ -97,27 +97,32 @@ def lib():
                                        ctypes.POINTER(ctypes.c_double)]
         L.sr_measure_fp64_peak.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
         L.sr_debug_pmatrix.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, _D]
-        L.sr_schedule_dump.argtypes = [ctypes.c_int32, _I32, _I32, _D, _I32, ctypes.c_int32, ctypes.c_int32,
+        L.sr_debug_cherry_table.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, _D]
+        L.sr_schedule_dump.argtypes = [ctypes.c_int32, _I32, _I32, _D, _I32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                        ctypes.c_int64, _I32, _I32, ctypes.POINTER(ctypes.c_int64),
                                        ctypes.POINTER(ctypes.c_int32)]
         _lib = L
     return _lib
 
 
-def schedule_dump(ft, rescale_every=8):
-    """Host-only: the fused pruning schedule for a FlatTree -> (steps[n,4] int32, node_slot[n_nodes], stack_depth)."""
+STEP_INTS = 8
+
+
+def schedule_dump(ft, rescale_every=8, cherry_tables=True):
+    """Host-only: the fused pruning schedule for a FlatTree -> (steps[n,8] int32, node_slot[n_nodes], stack_depth).
+    Step columns: word, alignment rows of gathers 0..2, second row of the step's cherry gather, 3 unused."""
     off = np.ascontiguousarray(ft.child_off, dtype=np.int32)
     idx = np.ascontiguousarray(ft.child_idx, dtype=np.int32)
     bl = np.ascontiguousarray(ft.blen, dtype=np.float64)
     lr = np.ascontiguousarray(ft.leaf_row, dtype=np.int32)
     cap = int(ft.n_nodes) + 8
-    steps = np.zeros((cap, 4), dtype=np.int32)
+    steps = np.zeros((cap, STEP_INTS), dtype=np.int32)
     node_slot = np.zeros(ft.n_nodes, dtype=np.int32)
     n = ctypes.c_int64()
     depth = ctypes.c_int32()
     rc = lib().sr_schedule_dump(int(ft.n_nodes), off.ctypes.data_as(_I32), idx.ctypes.data_as(_I32), bl.ctypes.data_as(_D),
-                                lr.ctypes.data_as(_I32), int(ft.root), int(rescale_every), cap, steps.ctypes.data_as(_I32),
-                                node_slot.ctypes.data_as(_I32), ctypes.byref(n), ctypes.byref(depth))
+                                lr.ctypes.data_as(_I32), int(ft.root), int(rescale_every), int(bool(cherry_tables)), cap,
+                                steps.ctypes.data_as(_I32), node_slot.ctypes.data_as(_I32), ctypes.byref(n), ctypes.byref(depth))
     if rc:
         raise SrError(rc, "sr_schedule_dump failed")
     return steps[:n.value].copy(), node_slot, depth.value
@@ -261,4 +266,10 @@ class Context:
     def debug_pmatrix(self, node, rate_class):
         out = np.zeros((20, 20))
         self._ck(lib().sr_debug_pmatrix(self._h, int(node), int(rate_class), out.ctypes.data_as(_D)))
+        return out
+
+    def debug_cherry_table(self, node, rate_class):
+        """[21, 21, 20]: the vector collapsed cherry `node` hands to its parent, per state pair of its two tips."""
+        out = np.zeros((21, 21, 20))
+        self._ck(lib().sr_debug_cherry_table(self._h, int(node), int(rate_class), out.ctypes.data_as(_D)))
         return out

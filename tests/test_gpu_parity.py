@@ -75,7 +75,15 @@ def test_cfg1_printed_output_identical(ctx, example_problem):
 def test_device_built_matrices_match_pal(ctx, example_problem):
     """K1 against `model.getTransitionProbabilities` (JointBranchReconstruction.java:217)."""
     p = example_problem
-    setup(ctx, p)
+    ctx.set_option("cherry_tables", 0)                                    # every edge keeps its own matrix in the stream
+    try:
+        setup(ctx, p)
+        _check_matrices(ctx, p)
+    finally:
+        ctx.set_option("cherry_tables", 1)
+
+
+def _check_matrices(ctx, p):
     worst = 0.0
     for v in range(1, p.flat.n_nodes):
         if v in p.tree.children[0]:
@@ -91,6 +99,37 @@ def test_device_built_matrices_match_pal(ctx, example_problem):
     # same operation order as PAL; only CUDA's exp() (<= 1 ulp) can differ. Off-diagonal entries of the 1e-6
     # branches are ~1e-8 and emerge from cancelling O(1) terms, so 1 ulp there is ~1e-10 relative.
     assert worst < 1e-9
+
+
+def test_cherry_tables_match_pal(ctx, example_problem):
+    """K1b: the table of a collapsed cherry against the reference's own arithmetic for that clade
+    (JointBranchReconstruction.java:208-230 with PAL's matrices): all 21 x 21 state pairs, missing data included."""
+    p = example_problem
+    setup(ctx, p)
+    _, node_slot, _ = native.schedule_dump(p.flat)
+    cherries = [v for v, s in enumerate(node_slot) if s <= -2]
+    assert len(cherries) >= 4
+    worst = 0.0
+    for v in cherries:
+        a, b = p.flat.child_idx[p.flat.child_off[v]:p.flat.child_off[v + 1]]
+        with pytest.raises(native.SrError):
+            ctx.debug_pmatrix(v, 0)                                       # its matrices are not in the stream any more
+        for k in (0, len(p.rates) - 1):
+            Pv, Pa, Pb = (oracle.transition_probs(p.model.Eval, p.model.Evec, p.model.Ievc, p.flat.blen[x] * p.rates[k]) for x in (v, a, b))
+            Ta = np.concatenate([Pa.T, Pa.sum(axis=1)[None, :]])          # [state or missing][k]
+            Tb = np.concatenate([Pb.T, Pb.sum(axis=1)[None, :]])
+            want = np.einsum("ik,ak,bk->abi", Pv, Ta, Tb)
+            got = ctx.debug_cherry_table(v, k)
+            worst = max(worst, float(np.max(np.abs(got - want) / want)))
+    assert worst < 1e-9
+    # and the two ways of pruning agree far inside the tolerance
+    with_tables = ctx.run()
+    try:
+        ctx.set_option("cherry_tables", 0)
+        without = ctx.run()
+    finally:
+        ctx.set_option("cherry_tables", 1)
+    assert rel_err(with_tables["lnl"], without["lnl"]) < 1e-12 and rel_err(with_tables["joint"], without["joint"]) < 1e-10
 
 
 @pytest.mark.parametrize("tile_m", [2, 4])
@@ -185,7 +224,8 @@ def test_cfg5_subset(ctx):
 @pytest.mark.parametrize("opts", [dict(tile_m=4), dict(tile_m=4, realloc=1), dict(tile_m=4, realloc=1, rotate=0), dict(warps=8), dict(warps=15),
                                   dict(warps=8, rotate=0), dict(holes=0), dict(holes=1), dict(holes=13), dict(holes=1234), dict(rotate=0),
                                   dict(warps=11), dict(warps=11, rotate=0), dict(warps=11, holes=0), dict(warps=11, holes=0, rotate=0),
-                                  dict(warps=11, prefetch=1), dict(warps=11, prefetch=1, rotate=0), dict(warps=12), dict(warps=12, rotate=0)])
+                                  dict(warps=11, prefetch=1), dict(warps=11, prefetch=1, rotate=0), dict(warps=12), dict(warps=12, rotate=0),
+                                  dict(cherry_tables=0), dict(cherry_tables=0, warps=11), dict(cherry_tables=0, tile_m=4), dict(cherry_table_mb=1)])
 def test_kernel_variants_agree(ctx, opts):
     """Every tuning variant of the pruning kernel (sr_set_option) gives oracle-exact results."""
     p = synthetic(3, 512)
@@ -197,7 +237,7 @@ def test_kernel_variants_agree(ctx, opts):
         r = ctx.run()
         assert rel_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
     finally:
-        for k, v in dict(tile_m=2, holes=2, rotate=1, prefetch=0).items():      # tile_m=2 restores the default warp layout
+        for k, v in dict(tile_m=2, holes=2, rotate=1, prefetch=0, cherry_tables=1, cherry_table_mb=1024).items():   # tile_m=2 restores the default warp layout
             ctx.set_option(k, v)
 
 

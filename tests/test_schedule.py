@@ -13,14 +13,20 @@ def built():
     native.build()
 
 
-def run_schedule(p, cols, rescale_every=8):
+def run_schedule(p, cols, rescale_every=8, cherry_tables=True):
     """Interpret the step list exactly as prune_kernel + root_kernel do (same flags, same slot order)."""
     ft = p.flat
-    steps, node_slot, depth = native.schedule_dump(ft, rescale_every)
+    steps, node_slot, depth = native.schedule_dump(ft, rescale_every, cherry_tables)
     slot_node = {int(s): v for v, s in enumerate(node_slot) if s >= 0}
+    cherry_node = {-2 - int(s): v for v, s in enumerate(node_slot) if s <= -2}       # collapsed cherries by table index
     assert sorted(slot_node) == list(range(len(slot_node)))                    # every edge exactly once, densely numbered
+    assert sorted(cherry_node) == list(range(len(cherry_node))) and (cherry_tables or not cherry_node)
     rc = ft.child_idx[ft.child_off[ft.root]:ft.child_off[ft.root + 1]]
-    assert len(slot_node) == ft.n_nodes - 1 - sum(1 for v in rc if ft.child_off[v] != ft.child_off[v + 1])
+    # every non-root edge is either in the matrix stream or inside a cherry table (3 edges each)
+    assert len(slot_node) + 3 * len(cherry_node) == ft.n_nodes - 1 - sum(1 for v in rc if ft.child_off[v] != ft.child_off[v + 1])
+    for v in cherry_node.values():
+        kids = ft.child_idx[ft.child_off[v]:ft.child_off[v + 1]]
+        assert len(kids) == 2 and all(ft.child_off[x] == ft.child_off[x + 1] for x in kids) and v not in rc
     m = p.model
     K = len(p.rates)
     lnl, joint = [], []
@@ -39,26 +45,41 @@ def run_schedule(p, cols, rescale_every=8):
                     return np.ones(20) if s >= 20 else np.eye(20)[s]
                 P = P_of(v)
                 return P.sum(axis=1) if s >= 20 else P[:, s]
+            def cherry(cid, row_a, row_b):
+                # what K1b tabulates: the cherry's own partial carried up its parent edge
+                v = cherry_node[cid]
+                a, b = ft.child_idx[ft.child_off[v]:ft.child_off[v + 1]]
+                return P_of(v) @ (tip(a, row_a) * tip(b, row_b))
             A, stack, cnt, slot, maxsp = None, [], 0, 0, 0
             parts = {}
-            for w, r0, r1, r2 in steps:
+            seen_cherries = 0
+            for w, r0, r1, r2, rb, _, _, _ in steps:
                 mv, n_pre, post = w & 3, (w >> 2) & 3, (w >> 5) & 1
+                ps, cid = (w >> 10) & 3, (int(w) & 0xffffffff) >> 13
+                assert ps <= n_pre + post
                 rows = [r0, r1, r2]
                 mv_node = None
                 if mv:
                     mv_node = slot_node[slot]; slot += 1
                 li = 0
-                for i in range(n_pre):
+
+                def gather():
+                    nonlocal slot, li, seen_cherries
+                    li += 1
+                    if ps == li:
+                        seen_cherries += 1
+                        return cherry(cid, rows[li - 1], rb)
                     v = slot_node[slot]; slot += 1
-                    t = tip(v, rows[li]); li += 1
+                    return tip(v, rows[li - 1])
+                for i in range(n_pre):
+                    t = gather()
                     A = t if (i == 0 and (w & 16)) else A * t
                 if mv:
                     A = P_of(mv_node) @ A
                     if mv == 2:
                         A = A * stack.pop()
                     if post:
-                        v = slot_node[slot]; slot += 1
-                        A = A * tip(v, rows[li])
+                        A = A * gather()
                 else:
                     assert not post
                 if w & 64:
@@ -72,7 +93,7 @@ def run_schedule(p, cols, rescale_every=8):
                     parts[0] = A
                 if w & 512:
                     parts[1] = A
-            assert not stack and slot == len(slot_node) and maxsp <= depth
+            assert not stack and slot == len(slot_node) and maxsp <= depth and seen_cherries == len(cherry_node)
             a, b = rc
             Pr = oracle.transition_probs(m.Eval, m.Evec, m.Ievc, (ft.blen[a] + ft.blen[b]) * p.rates[k])
             per_rate.append((m.pi * parts[0])[:, None] * Pr * parts[1][None, :])
@@ -89,11 +110,16 @@ def test_schedule_on_example(example_problem):
     p = example_problem
     lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
     cols = [0, 13, 40, 129]
-    got_l, got_j, steps, depth = run_schedule(p, cols)
+    got_l, got_j, steps, depth = run_schedule(p, cols, cherry_tables=False)
     assert rel_err(got_l, lnl[cols]) < 1e-12 and rel_err(got_j, joint[cols]) < 1e-9
     assert depth == 2 and len(steps) < 34                       # fused: fewer steps than the 34 edges
     mv_steps = int(np.count_nonzero(steps[:, 0] & 3))
     assert mv_steps == 15                                       # one MV per internal edge below the root children (E_int = N-4)
+    # with cherry tables every collapsed cherry's contraction is gone, the results are the same
+    got_l, got_j, steps_c, depth_c = run_schedule(p, cols)
+    assert rel_err(got_l, lnl[cols]) < 1e-12 and rel_err(got_j, joint[cols]) < 1e-9
+    n_cherry = int(np.count_nonzero((steps_c[:, 0] >> 10) & 3))
+    assert n_cherry >= 4 and int(np.count_nonzero(steps_c[:, 0] & 3)) == 15 - n_cherry and depth_c <= depth
 
 
 def test_schedule_shapes():
@@ -120,10 +146,11 @@ def test_schedule_shapes():
             rates1 = np.array([1.0])
             p.rates = rates1                                   # the reference only handles this shape for K = 1
         lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
-        got_l, got_j, steps, depth = run_schedule(p, range(6))
-        assert rel_err(got_l, lnl) < 1e-12 and rel_err(got_j, joint) < 1e-9, nw
-        got_l, got_j, _, _ = run_schedule(p, range(2), rescale_every=1)
-        assert rel_err(got_l, lnl[:2]) < 1e-12
+        for ct in (True, False):
+            got_l, got_j, steps, depth = run_schedule(p, range(6), cherry_tables=ct)
+            assert rel_err(got_l, lnl) < 1e-12 and rel_err(got_j, joint) < 1e-9, nw
+            got_l, got_j, _, _ = run_schedule(p, range(2), rescale_every=1, cherry_tables=ct)
+            assert rel_err(got_l, lnl[:2]) < 1e-12
 
 
 @pytest.mark.parametrize("kind,n,depth_max", [("balanced", 64, 5), ("yule", 200, 6), ("caterpillar", 300, 0)])
@@ -137,8 +164,15 @@ def test_schedule_synthetic(kind, n, depth_max):
     p.rates = oracle.gamma_rates(2, 0.5)
     p.states = synth.simulate_alignment(tree, p.model, p.rates, 3, seed=9)
     lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
-    got_l, got_j, steps, depth = run_schedule(p, range(3))
+    got_l, got_j, steps, depth = run_schedule(p, range(3), cherry_tables=False)
     assert rel_err(got_l, lnl) < 1e-12 and rel_err(got_j, joint) < 1e-9
     assert depth <= depth_max
     n_mv = int(np.count_nonzero(steps[:, 0] & 3))
     assert len(steps) <= n_mv + 4 + (0 if kind != "balanced" else n // 2)      # nearly every step carries an MMA burst
+    got_l, got_j, steps_c, depth_c = run_schedule(p, range(3))
+    assert rel_err(got_l, lnl) < 1e-12 and rel_err(got_j, joint) < 1e-9 and depth_c <= depth
+    n_cherry = int(np.count_nonzero((steps_c[:, 0] >> 10) & 3))
+    n_mv_c = int(np.count_nonzero(steps_c[:, 0] & 3))
+    assert n_mv_c == n_mv - n_cherry
+    assert n_cherry >= {"balanced": n // 2 - 2, "yule": n // 4, "caterpillar": 1}[kind]
+    print(kind, "steps", len(steps), "->", len(steps_c), "contractions", n_mv, "->", n_mv_c)
