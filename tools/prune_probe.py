@@ -19,6 +19,7 @@ ap.add_argument("--holes", type=int, default=-1)
 ap.add_argument("--rotate", type=int, default=-1)
 ap.add_argument("--prefetch", type=int, default=-1)
 ap.add_argument("--rescale", type=int, default=0)
+ap.add_argument("--debug", type=int, default=0)
 ap.add_argument("--taxa", type=int, default=1000)
 ap.add_argument("--tree", default="yule")
 ap.add_argument("--ncat", type=int, default=4)
@@ -50,6 +51,8 @@ if a.warps == 13:
     ctx.set_option("realloc", 1)
 elif a.warps:
     ctx.set_option("warps", a.warps)
+if a.debug:
+    ctx.set_option("debug", a.debug)
 ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
 ctx.set_rates(rates)
 ctx.set_tree(treeio.flatten_tree(tree))
