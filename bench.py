@@ -212,6 +212,12 @@ def run_b200(a):
     ctx.set_tree(flat)
     info = ctx.schedule_info()
     flops_per_col = info["flops_per_column_rate"] * len(rates)
+    # Cherry tables: a collapsed cherry's two tip products and its 20x20 contraction (2*20 + 820 algorithmic flops per
+    # column and rate class) are replaced by one 20-flop gather product. `achieved` below stays ALGORITHMIC (SURVEY
+    # §8d: what the reference's arithmetic costs); `executed` counts only what the kernel still computes per column.
+    _, node_slot, _ = native.schedule_dump(flat)
+    n_cherry = int(np.count_nonzero(node_slot <= -2))
+    executed_per_col = flops_per_col - len(rates) * n_cherry * (820.0 + 20.0)
 
     # host (pinned) copies of the step's inputs and outputs
     h_states = native.PinnedArray((N, L), np.uint8)
@@ -332,6 +338,12 @@ def run_b200(a):
                          "kernel": "prune_kernel (FP64 DMMA m8n8k4)", "kernel_ms": k2_ms,
                          "kernel_share_of_step": prof["ms_prune"] / ms if world == 1 else None,
                          "flops_per_column": flops_per_col,
+                         "executed": achieved * executed_per_col / flops_per_col,
+                         "frac_executed": achieved * executed_per_col / flops_per_col / peak_tflops,
+                         "executed_note": f"{n_cherry} of the tree's cherries are tabulated per state pair once per rate class (K1b) "
+                                          "and gathered instead of contracted per column: `achieved`/`frac` count the algorithmic "
+                                          "flops of SURVEY 8d, `executed`/`frac_executed` only the flops prune_kernel still performs "
+                                          "per column (its tensor-pipe efficiency; ceiling 0.83 from the 20->24 padding)",
                          "peak_source": "live DMMA probe (sr_measure_fp64_peak) on this GPU; MEASURED_PEAKS.json has no FP64 entry; "
                                         "nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s"},
             "e2e": e2e, "e2e_compact": e2e_compact, "numa_node": numa_node, "gpu_launches": launches,
