@@ -357,10 +357,11 @@ enum : int32_t {
     STF_STORE_A = 1 << 8,
     STF_STORE_B = 1 << 9,
     STF_ANY = STF_RESCALE | STF_PUSH | STF_STORE_A | STF_STORE_B,
-    ST_PSEUDO_SHIFT = 10,    // bits 10-11: 1-based position (among the step's gathers) of its cherry-table gather, 0 = none
-    ST_CHERRY_SHIFT = 13     // bits 13-31: index of that cherry's table
+    ST_PSEUDO_SHIFT = 10,    // bits 10-11: 1-based position (among the step's gathers) of its first cherry-table gather, 0 = none
+    ST_PSEUDO2_SHIFT = 12,   // bits 12-13: position of a second one (0 = none); its table is the next one (index + 1)
+    ST_CHERRY_SHIFT = 14     // bits 14-31: index of the first cherry's table
 };
-constexpr int STEP_INTS = 8;                  // {word, row of gather 0, 1, 2}, {second row of the cherry gather, 0, 0, 0}
+constexpr int STEP_INTS = 8;                  // {word, row of gather 0, 1, 2}, {second rows of the two cherry gathers, 0, 0}
 
 struct PruneParams {
     const int4* steps;         // [n_steps][2] {word, row of gather 0, 1, 2}, {second row of the cherry gather, -, -, -}
@@ -400,7 +401,7 @@ struct PruneCfg {
     static constexpr int LEVEL_DOUBLES = W * M * 5 * 32;
     static constexpr int LEVEL_BYTES = LEVEL_DOUBLES * 8;
     static constexpr int STATES_OFF = FRAG_BYTES + 3 * TABLE_BYTES;                 // 13920
-    static constexpr int STAGE_BYTES = ((STATES_OFF + 4 * S + 127) / 128) * 128;    // 3 gather rows + the cherry gather's second row
+    static constexpr int STAGE_BYTES = ((STATES_OFF + 5 * S + 127) / 128) * 128;    // 3 gather rows + the second rows of up to two cherry gathers
 };
 
 __host__ __device__ constexpr int prune_bar_bytes(int nstage) { return ((2 * nstage * 8 + 127) / 128) * 128; }
@@ -441,7 +442,8 @@ __host__ __device__ constexpr int pairs_before(int kstep) { return kstep >= 5 ? 
 
 constexpr int prune_threads(int w, bool inl, bool ra) { return ra ? (w + 4) * 32 : (w + (inl ? 0 : 1)) * 32; }
 
-template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false, bool RA = false>
+// TWOPS: steps may carry two cherry gathers (schedules of trees with many pairs of sibling cherries).
+template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false, bool RA = false, bool TWOPS = false>
 __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(PruneParams p) {
     static_assert(!RA || (!INL && ((W_ == 12 && M == 2) || (W_ == 8 && M == 4))), "register re-allocation is laid out for 12 x M=2 or 8 x M=4 consumer warps");
     using Cfg = PruneCfg<M, W_>;
@@ -469,19 +471,21 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
     uint32_t it = 0;                                  // ring position, runs on across work items
 
     // issue the TMA copies of one step (global ring position itp; work item `item_p`, step `step_p`) — one thread
-    auto issue_step = [&](uint32_t itp, int item_p, const int4 d, const int row_b, const int off_d, bool wait_empty) {
+    auto issue_step = [&](uint32_t itp, int item_p, const int4 d, const int2 row_b, const int off_d, bool wait_empty) {
         const int kp = item_p / p.n_tiles, tilep = item_p - kp * p.n_tiles;
         const double* ps = p.pstream + (size_t)kp * p.rate_stride;
         const uint8_t* st = p.states + p.col0 + (int64_t)tilep * S;
         const int stage = itp % NSTAGE;
         const uint32_t ph = (itp / NSTAGE) & 1;
         const int n_leaf = ((d.x >> ST_NPRE_SHIFT) & 3) + ((d.x & ST_NPOST) ? 1 : 0);
-        const int pseudo = ((d.x >> ST_PSEUDO_SHIFT) & 3) ? 1 : 0;          // a cherry gather brings a second state row, no table
+        // a cherry gather brings a second state row and no table
+        const int pseudo = (((d.x >> ST_PSEUDO_SHIFT) & 3) ? 1 : 0) + (((d.x >> ST_PSEUDO2_SHIFT) & 3) ? 1 : 0);
         const uint32_t pbytes = ((d.x & ST_MV_MASK) ? FRAG_BYTES : 0) + (n_leaf - pseudo) * TABLE_BYTES;
         if (wait_empty) mbar_wait(&empty[stage], ph ^ 1);
         unsigned char* dst = stages + stage * STAGE_BYTES;
         mbar_expect_tx(&full[stage], pbytes + (n_leaf + pseudo) * S);
-        if (pseudo) bulk_g2s(dst + Cfg::STATES_OFF + 3 * S, st + (int64_t)row_b * p.pitch, S, &full[stage]);
+        if (pseudo > 0) bulk_g2s(dst + Cfg::STATES_OFF + 3 * S, st + (int64_t)row_b.x * p.pitch, S, &full[stage]);
+        if (pseudo > 1) bulk_g2s(dst + Cfg::STATES_OFF + 4 * S, st + (int64_t)row_b.y * p.pitch, S, &full[stage]);
         if (pbytes) bulk_g2s(dst, ps + off_d, pbytes, &full[stage]);
         if (n_leaf > 0) bulk_g2s(dst + Cfg::STATES_OFF, st + (int64_t)d.y * p.pitch, S, &full[stage]);
         if (n_leaf > 1) bulk_g2s(dst + Cfg::STATES_OFF + S, st + (int64_t)d.z * p.pitch, S, &full[stage]);
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
         if (lane == 0) {
             for (int item = blockIdx.x; item < n_items; item += gridDim.x)
                 for (int step = 0; step < p.n_steps; ++step, ++it)
-                    issue_step(it, item, __ldg(p.steps + 2 * step), __ldg(&p.steps[2 * step + 1].x), __ldg(p.step_off + step), true);
+                    issue_step(it, item, __ldg(p.steps + 2 * step), __ldg(reinterpret_cast<const int2*>(p.steps + 2 * step + 1)), __ldg(p.step_off + step), true);
         }
     };
     if (RA) {
@@ -526,10 +530,11 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
     uint32_t my_pos = (uint32_t)warp;
     int my_item = blockIdx.x, my_step = warp;
     int4 my_d = make_int4(0, 0, 0, 0);
-    int my_off = 0, my_rowb = 0;
+    int my_off = 0;
+    int2 my_rowb = make_int2(0, 0);
     auto my_normalise = [&]() {
         while (my_item < n_items && my_step >= p.n_steps) { my_step -= p.n_steps; my_item += gridDim.x; }
-        if (my_item < n_items) { my_d = __ldg(p.steps + 2 * my_step); my_rowb = __ldg(&p.steps[2 * my_step + 1].x); my_off = __ldg(p.step_off + my_step); }
+        if (my_item < n_items) { my_d = __ldg(p.steps + 2 * my_step); my_rowb = __ldg(reinterpret_cast<const int2*>(p.steps + 2 * my_step + 1)); my_off = __ldg(p.step_off + my_step); }
     };
     // try (or, if `block`, wait) to refill my next position; returns after at most one refill
     auto my_refill = [&](bool block) {
@@ -646,8 +651,9 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
             // ---- tips below this node (gathers of P^T rows by observed state): loads first ...
             // At most one of the step's gathers is a collapsed cherry (position ps, 1-based): its row, selected by the state
             // PAIR of the cherry's two tips, comes from the cherry's table in global memory (L2) instead of the stage.
-            const int ps = (w >> ST_PSEUDO_SHIFT) & 3;
+            const int ps = (w >> ST_PSEUDO_SHIFT) & 3, ps2 = TWOPS ? ((w >> ST_PSEUDO2_SHIFT) & 3) : 0;
             const double* crow[M];
+            const double* crow2[TWOPS ? M : 1];
             if (ps) {
                 const unsigned cid = (unsigned)w >> ST_CHERRY_SHIFT;
 #pragma unroll
@@ -656,17 +662,30 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
                     const int sb = stb[3 * S + j * 8];
                     crow[j] = ctab_k + ((size_t)cid * CHERRY_ROWS + sa * 21 + sb) * CHERRY_ROW_DOUBLES;
                 }
+                if (TWOPS && ps2) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) {
+                        const int sa = ps2 == 2 ? s1[j] : s2[j];
+                        const int sb = stb[4 * S + j * 8];
+                        crow2[TWOPS ? j : 0] = ctab_k + ((size_t)(cid + 1) * CHERRY_ROWS + sa * 21 + sb) * CHERRY_ROW_DOUBLES;
+                    }
+                }
             }
+            auto gload = [&](double (&dst)[M][5], const double* const* rows) {
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    double pad;
+                    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(dst[j][0]), "=d"(dst[j][1]) : "l"(rows[j]));
+                    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+16];" : "=d"(dst[j][2]), "=d"(dst[j][3]) : "l"(rows[j]));
+                    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+32];" : "=d"(dst[j][4]), "=d"(pad) : "l"(rows[j]));
+                }
+            };
             // gather number `pos` (1-based) of the step; `tix` = index of its table among the step's staged tables
             auto gather = [&](double (&dst)[M][5], const int (&sx)[M], int pos, int tix) {
                 if (ps == pos) {
-#pragma unroll
-                    for (int j = 0; j < M; ++j) {
-                        double pad;
-                        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(dst[j][0]), "=d"(dst[j][1]) : "l"(crow[j]));
-                        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+16];" : "=d"(dst[j][2]), "=d"(dst[j][3]) : "l"(crow[j]));
-                        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+32];" : "=d"(dst[j][4]), "=d"(pad) : "l"(crow[j]));
-                    }
+                    gload(dst, crow);
+                } else if (TWOPS && ps2 == pos) {
+                    gload(dst, crow2);
                 } else {
 #pragma unroll
                     for (int j = 0; j < M; ++j) {
@@ -678,11 +697,11 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
             };
             double tp0[M][5], tp1[M][5];
             if (n_pre >= 1) gather(tp0, s0, 1, 0);
-            if (n_pre == 2) gather(tp1, s1, 2, ps == 1 ? 0 : 1);
+            if (n_pre == 2) gather(tp1, s1, 2, ps == 1 ? 0 : 1);                 // (staged tables skip the cherry gathers)
             int spost[M];
 #pragma unroll
             for (int j = 0; j < M; ++j) spost[j] = n_pre == 0 ? s0[j] : (n_pre == 1 ? s1[j] : s2[j]);
-            const int post_tix = n_pre - ((ps && ps <= n_pre) ? 1 : 0);
+            const int post_tix = n_pre - ((ps && ps <= n_pre) ? 1 : 0) - ((ps2 && ps2 <= n_pre) ? 1 : 0);
             double vp[M][5];
             if (mv && (w & ST_NPOST) && !LAZY) gather(vp, spost, n_pre + 1, post_tix);
             // The post-MMA operands are only consumed after the burst. Pin them here so the compiler cannot sink their loads
@@ -690,7 +709,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
             // burst, and a load from it that is still in flight then races the TMA refill (seen as 1-in-10 runs with a few
             // columns off by 1e-5 at 5,000 taxa; tests/test_gpu_parity.py::*full_size*, tools/stress_big.py).
             if (!LAZY && mv) {
-                if ((w & ST_NPOST) && ps != n_pre + 1) {       // (a cherry row comes from global memory: it may stay in flight)
+                if ((w & ST_NPOST) && ps != n_pre + 1 && ps2 != n_pre + 1) {   // (a cherry row comes from global memory: it may stay in flight)
 #pragma unroll
                     for (int j = 0; j < M; ++j)
 #pragma unroll

@@ -80,6 +80,8 @@ struct sr_ctx {
     int tile_m = 2;
     int debug = 0;
     int holes = 2;                      // pauses inside a warp's MMA burst (0..2), see kernels.cuh
+    int cherry_pairs = 1;               // let one step gather two cherries (siblings): trees with many cherry pairs
+    bool has_pairs = false;             // the current schedule contains such steps (selects the kernel variant)
     int cherry_tables = 1;              // collapse cherries into 441-row lookup tables (see build_schedule)
     int64_t cherry_table_mb = 1024;     // memory cap for those tables; cherries beyond it are pruned the ordinary way
     bool input_chars = false;           // alignment bytes are residue letters, translated on the device
@@ -168,7 +170,7 @@ int build_schedule(sr_ctx* c) {
     c->cherry_node.clear(); c->cherry_blen.clear();
     if (c->cherry_tables && !c->prefetch) {
         const int64_t per = (int64_t)std::max(1, c->K) * CHERRY_ROWS * CHERRY_ROW_DOUBLES * (int64_t)sizeof(double);
-        const int64_t cap = std::min<int64_t>((c->cherry_table_mb << 20) / per, (1 << 19) - 1);
+        const int64_t cap = std::min<int64_t>((c->cherry_table_mb << 20) / per, (1 << 18) - 2);
         for (int v = 0; v < n && (int64_t)c->cherry_node.size() < cap; ++v) {
             if (v == c->root || v == rc0 || v == rc1 || off[v + 1] - off[v] != 2) continue;
             const int a = idx[off[v]], b = idx[off[v] + 1];
@@ -232,8 +234,27 @@ int build_schedule(sr_ctx* c) {
         (which == 0 ? prims.back().store_a : prims.back().store_b) = true;
     }
 
+    // cherry tables are numbered in the order the schedule uses them, so that two cherry gathers of one step have
+    // consecutive indices (the step word carries only the first)
+    {
+        std::vector<int32_t> nodes;
+        std::vector<double> lens;
+        for (const Prim& pr : prims) {
+            if (pr.code > P_LEAF_MUL || cherry_of[pr.child] < 0) continue;
+            const int old_id = cherry_of[pr.child];
+            cherry_of[pr.child] = (int32_t)nodes.size();
+            nodes.push_back(pr.child);
+            for (int t = 0; t < 3; ++t) lens.push_back(c->cherry_blen[3 * old_id + t]);
+        }
+        c->cherry_node.swap(nodes);
+        c->cherry_blen.swap(lens);
+    }
+    // (two cherry gathers per step only for the default kernel layout: the tuning variants are single-gather builds)
+    const bool default_layout = c->tile_m == 2 && c->warps == 12 && c->realloc && !c->prefetch && c->holes == 2;
+    const int max_pseudo = (c->cherry_pairs && default_layout) ? 2 : 1;
     // ---- fuse into steps: [<=2 tip gathers] [one MV] [<=1 tip gather]; a push/store ends its step
     c->steps.clear(); c->step_off.clear();
+    c->has_pairs = false;
     c->slot_kind.clear(); c->slot_off.clear(); c->slot_blen.clear();
     c->node_slot.assign(n, -1);
     c->e_int = c->e_leaf = 0;
@@ -261,17 +282,18 @@ int build_schedule(sr_ctx* c) {
     };
     size_t i = 0;
     while (i < prims.size()) {
-        int32_t word = 0, rows[3] = {0, 0, 0}, row_b = 0;
+        int32_t word = 0, rows[3] = {0, 0, 0}, row_b[2] = {0, 0};
         int n_leaf = 0, n_pre = 0;
-        int pseudo_at = 0;                       // 1-based gather position of the step's cherry-table gather (at most one)
+        int n_pseudo = 0;                        // cherry-table gathers of this step (at most max_pseudo)
         auto is_pseudo = [&](const Prim& pr) { return pr.code <= P_LEAF_MUL && cherry_of[pr.child] >= 0; };
         auto take_gather = [&](const Prim& pr) {
             if (is_pseudo(pr)) {
                 const int a = idx[off[pr.child]], b = idx[off[pr.child] + 1];
                 rows[n_leaf++] = c->leaf_row[a];
-                row_b = c->leaf_row[b];
-                pseudo_at = n_leaf;
-                word |= (pseudo_at << ST_PSEUDO_SHIFT) | (cherry_of[pr.child] << ST_CHERRY_SHIFT);
+                row_b[n_pseudo] = c->leaf_row[b];
+                if (n_pseudo == 0) word |= (n_leaf << ST_PSEUDO_SHIFT) | (cherry_of[pr.child] << ST_CHERRY_SHIFT);
+                else word |= n_leaf << ST_PSEUDO2_SHIFT;
+                ++n_pseudo;
                 ++s_cur;                         // two edges deep
             } else {
                 rows[n_leaf++] = c->leaf_row[pr.child];
@@ -282,10 +304,10 @@ int build_schedule(sr_ctx* c) {
         // the step's matrices are laid out [MV fragments][tables...] — find the MV (if any) first
         size_t j = i;
         int pre = 0;
-        bool seen_pseudo = false;
+        int seen_pseudo = 0;
         while (j < prims.size() && prims[j].code <= P_LEAF_MUL && pre < 2 && !(j > i && prims[j].code == P_LEAF_SET) &&
-               !(seen_pseudo && is_pseudo(prims[j]))) {
-            seen_pseudo = seen_pseudo || is_pseudo(prims[j]);
+               !(seen_pseudo >= max_pseudo && is_pseudo(prims[j]))) {
+            seen_pseudo += is_pseudo(prims[j]) ? 1 : 0;
             ++pre; ++j;
             if (prims[j - 1].push || prims[j - 1].store_a || prims[j - 1].store_b) { ended = true; break; }
         }
@@ -310,7 +332,7 @@ int build_schedule(sr_ctx* c) {
             last = &pr;
             i = mv_at + 1;
             ended = pr.push || pr.store_a || pr.store_b;
-            if (!ended && i < prims.size() && prims[i].code == P_LEAF_MUL && !(pseudo_at && is_pseudo(prims[i]))) {
+            if (!ended && i < prims.size() && prims[i].code == P_LEAF_MUL && !(n_pseudo >= max_pseudo && is_pseudo(prims[i]))) {
                 const Prim& pl = prims[i];
                 add_slot(pl);
                 take_gather(pl);
@@ -327,7 +349,8 @@ int build_schedule(sr_ctx* c) {
         if (last->store_b) word |= STF_STORE_B;
         c->steps.push_back(word);
         c->steps.push_back(rows[0]); c->steps.push_back(rows[1]); c->steps.push_back(rows[2]);
-        c->steps.push_back(row_b); c->steps.push_back(0); c->steps.push_back(0); c->steps.push_back(0);
+        c->steps.push_back(row_b[0]); c->steps.push_back(row_b[1]); c->steps.push_back(0); c->steps.push_back(0);
+        if (n_pseudo > 1) c->has_pairs = true;
         if (off_d > INT32_MAX - 4096) return fail(c, SR_ERR_UNSUPPORTED, "tree too large for 32-bit matrix-stream offsets");
     }
     c->rate_stride = off_d;
@@ -418,7 +441,7 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     return SR_OK;
 }
 
-template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false, bool RA = false>
+template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false, bool RA = false, bool TWOPS = false>
 int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     using Cfg = PruneCfg<M, W>;
     const int fixed = NSTAGE * Cfg::STAGE_BYTES + prune_bar_bytes(NSTAGE);
@@ -433,7 +456,7 @@ int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     p.spill_levels = spill_levels;
     p.spill = c->d_spill.as<double>();
     const int smem = fixed + levels * Cfg::LEVEL_BYTES;
-    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT, PREF, INL, RA>;
+    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT, PREF, INL, RA, TWOPS>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prof_begin(c, s, 1, cols);
     kern<<<grid, prune_threads(W, INL, RA), smem, s>>>(p);
@@ -480,7 +503,14 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
 #endif
     // kernel variants: tile_m (column tiles per warp), consumer warps, holes in the MMA burst, burst rotation
     const int hl = c->holes, rot = c->rotate;
-    if (c->tile_m == 4 && c->realloc) rc = rot ? launch_prune<4, 4, 8, 2, true, false, false, true>(c, s, p, n) : launch_prune<4, 4, 8, 0, false, false, false, true>(c, s, p, n);
+    if (c->has_pairs) {
+        // schedules with two cherry gathers in a step run on the default layout's two-gather build (the tuning variants
+        // below are single-gather builds; "cherry_pairs" = 0 gives them a schedule they can run)
+        if (!(c->tile_m == 2 && c->warps == 12 && c->realloc && !c->prefetch && hl == 2))
+            return fail(c, SR_ERR_UNSUPPORTED, "internal: schedule with cherry pairs on a single-gather kernel variant");
+        rc = rot ? launch_prune<2, 4, 12, 2, true, false, false, true, true>(c, s, p, n)
+                 : launch_prune<2, 4, 12, 2, false, false, false, true, true>(c, s, p, n);
+    } else if (c->tile_m == 4 && c->realloc) rc = rot ? launch_prune<4, 4, 8, 2, true, false, false, true>(c, s, p, n) : launch_prune<4, 4, 8, 0, false, false, false, true>(c, s, p, n);
     else if (c->tile_m == 4) rc = launch_prune<4, 4, 8>(c, s, p, n);
     else if (c->warps == 12 && c->realloc && rot && hl == 0) rc = launch_prune<2, 4, 12, 0, true, false, false, true>(c, s, p, n);
     else if (c->warps == 12 && c->realloc && rot && hl == 1) rc = launch_prune<2, 4, 12, 1, true, false, false, true>(c, s, p, n);
@@ -943,27 +973,34 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
         c->tile_m = (int)value;
         c->warps = (value == 4) ? 8 : 12;
         c->realloc = (value == 2);
+        c->sched_dirty = true;
     } else if (k == "warps") {
         // register files are allocated in 4-warp granules: with the producer warp, 11 and 15 consumers are "free"
         if (value != 8 && value != 11 && value != 12 && value != 15) return fail(c, SR_ERR_ARG, "warps must be 8, 11, 12 or 15");
         if (c->tile_m == 4 && value != 8) return fail(c, SR_ERR_ARG, "tile_m 4 supports 8 warps only");
         c->warps = (int)value;
         c->realloc = false;
+        c->sched_dirty = true;
     } else if (k == "realloc") {
         // dedicated producer warp living on re-allocated registers (setmaxnreg): 12 consumers x tile_m 2, or 8 x tile_m 4
         c->realloc = value != 0;
         if (c->realloc) c->warps = (c->tile_m == 4) ? 8 : 12;
+        c->sched_dirty = true;
     } else if (k == "chunk_cols") {
         if (value < 256) return fail(c, SR_ERR_ARG, "chunk_cols must be >= 256");
         c->chunk_cols = (value + 255) / 256 * 256;
     } else if (k == "holes") {
         if (value < 0 || value > 1234) return fail(c, SR_ERR_ARG, "holes must be 0, 1, 2 or the digits of the k-steps (1..4) to pause before");
         c->holes = (int)value;
+        c->sched_dirty = true;
     } else if (k == "compress_patterns") {
         c->compress = value != 0;
         c->last_unique = c->last_total = 0;
     } else if (k == "cherry_tables") {
         c->cherry_tables = value != 0;
+        c->sched_dirty = true;
+    } else if (k == "cherry_pairs") {
+        c->cherry_pairs = value != 0;
         c->sched_dirty = true;
     } else if (k == "cherry_table_mb") {
         if (value < 0) return fail(c, SR_ERR_ARG, "cherry_table_mb must be >= 0");

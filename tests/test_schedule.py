@@ -53,10 +53,10 @@ def run_schedule(p, cols, rescale_every=8, cherry_tables=True):
             A, stack, cnt, slot, maxsp = None, [], 0, 0, 0
             parts = {}
             seen_cherries = 0
-            for w, r0, r1, r2, rb, _, _, _ in steps:
+            for w, r0, r1, r2, rb, rb2, _, _ in steps:
                 mv, n_pre, post = w & 3, (w >> 2) & 3, (w >> 5) & 1
-                ps, cid = (w >> 10) & 3, (int(w) & 0xffffffff) >> 13
-                assert ps <= n_pre + post
+                ps, ps2, cid = (w >> 10) & 3, (w >> 12) & 3, (int(w) & 0xffffffff) >> 14
+                assert ps <= n_pre + post and (ps2 == 0 or ps < ps2 <= n_pre + post)
                 rows = [r0, r1, r2]
                 mv_node = None
                 if mv:
@@ -66,9 +66,9 @@ def run_schedule(p, cols, rescale_every=8, cherry_tables=True):
                 def gather():
                     nonlocal slot, li, seen_cherries
                     li += 1
-                    if ps == li:
+                    if ps == li or ps2 == li:                              # the second one uses the next table
                         seen_cherries += 1
-                        return cherry(cid, rows[li - 1], rb)
+                        return cherry(cid + (ps2 == li), rows[li - 1], rb2 if ps2 == li else rb)
                     v = slot_node[slot]; slot += 1
                     return tip(v, rows[li - 1])
                 for i in range(n_pre):
@@ -118,7 +118,7 @@ def test_schedule_on_example(example_problem):
     # with cherry tables every collapsed cherry's contraction is gone, the results are the same
     got_l, got_j, steps_c, depth_c = run_schedule(p, cols)
     assert rel_err(got_l, lnl[cols]) < 1e-12 and rel_err(got_j, joint[cols]) < 1e-9
-    n_cherry = int(np.count_nonzero((steps_c[:, 0] >> 10) & 3))
+    n_cherry = int(np.count_nonzero((steps_c[:, 0] >> 10) & 3) + np.count_nonzero((steps_c[:, 0] >> 12) & 3))
     assert n_cherry >= 4 and int(np.count_nonzero(steps_c[:, 0] & 3)) == 15 - n_cherry and depth_c <= depth
 
 
@@ -171,7 +171,7 @@ def test_schedule_synthetic(kind, n, depth_max):
     assert len(steps) <= n_mv + 4 + (0 if kind != "balanced" else n // 2)      # nearly every step carries an MMA burst
     got_l, got_j, steps_c, depth_c = run_schedule(p, range(3))
     assert rel_err(got_l, lnl) < 1e-12 and rel_err(got_j, joint) < 1e-9 and depth_c <= depth
-    n_cherry = int(np.count_nonzero((steps_c[:, 0] >> 10) & 3))
+    n_cherry = int(np.count_nonzero((steps_c[:, 0] >> 10) & 3) + np.count_nonzero((steps_c[:, 0] >> 12) & 3))
     n_mv_c = int(np.count_nonzero(steps_c[:, 0] & 3))
     assert n_mv_c == n_mv - n_cherry
     assert n_cherry >= {"balanced": n // 2 - 2, "yule": n // 4, "caterpillar": 1}[kind]
