@@ -216,8 +216,14 @@ def run_b200(a):
     # column and rate class) are replaced by one 20-flop gather product. `achieved` below stays ALGORITHMIC (SURVEY
     # §8d: what the reference's arithmetic costs); `executed` counts only what the kernel still computes per column.
     _, node_slot, _ = native.schedule_dump(flat)
-    n_cherry = int(np.count_nonzero(node_slot <= -2))
-    executed_per_col = flops_per_col - len(rates) * n_cherry * (820.0 + 20.0)
+    n_cherry = n_fork = 0
+    for v in np.nonzero(node_slot <= -2)[0]:
+        kids = flat.child_idx[flat.child_off[v]:flat.child_off[v + 1]]
+        if all(flat.child_off[x] == flat.child_off[x + 1] for x in kids):
+            n_cherry += 1                  # two tip products + one contraction -> one gather product
+        else:
+            n_fork += 1                    # (cherry, tip): three tip products + two contractions -> one gather product
+    executed_per_col = flops_per_col - len(rates) * (n_cherry * (820.0 + 20.0) + n_fork * (2 * 820.0 + 2 * 20.0))
 
     # host (pinned) copies of the step's inputs and outputs
     h_states = native.PinnedArray((N, L), np.uint8)
@@ -340,8 +346,8 @@ def run_b200(a):
                          "flops_per_column": flops_per_col,
                          "executed": achieved * executed_per_col / flops_per_col,
                          "frac_executed": achieved * executed_per_col / flops_per_col / peak_tflops,
-                         "executed_note": f"{n_cherry} of the tree's cherries are tabulated per state pair once per rate class (K1b) "
-                                          "and gathered instead of contracted per column: `achieved`/`frac` count the algorithmic "
+                         "executed_note": f"{n_cherry} cherries and {n_fork} pitchforks (cherry + tip) of the tree are tabulated per state "
+                                          "combination once per rate class (K1b) and gathered instead of contracted per column: `achieved`/`frac` count the algorithmic "
                                           "flops of SURVEY 8d, `executed`/`frac_executed` only the flops prune_kernel still performs "
                                           "per column (its tensor-pipe efficiency; ceiling 0.83 from the 20->24 padding)",
                          "peak_source": "live DMMA probe (sr_measure_fp64_peak) on this GPU; MEASURED_PEAKS.json has no FP64 entry; "

@@ -117,8 +117,9 @@ void sr_host_free(void *p);
  * result to its duplicates; off by default), "prefetch" (experimental), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage), "stream_taper" (0/1: short pipeline
  * chunks at both ends of a streamed run, on by default), "input_chars" (0/1: alignment bytes are residue letters, see
  * sr_set_alignment), "cherry_tables" (0/1, default 1: tabulate every cherry's contribution per state pair once per rate
- * class and gather it instead of contracting it per column) with "cherry_table_mb" (memory cap, default 1024) and
- * "cherry_pairs" (0/1, default 1: a step may gather two sibling cherries), "realloc" (0/1, experimental: producer warp on re-allocated registers, 12 x tile_m 2 or
+ * class and gather it instead of contracting it per column) with "cherry_table_mb" (memory cap, default 4096) "cherry_pairs"
+ * (0/1, default 1: a step may gather two such clades) and "cherry_pitchforks" (0/1, default 1: the same one level up, a
+ * cherry plus a tip, 9261 state triples), "realloc" (0/1, experimental: producer warp on re-allocated registers, 12 x tile_m 2 or
  * 8 x tile_m 4 consumer warps), "profile"
  * (0/1: record per-kernel events), "rescale_every" (edges between power-of-two rescalings). */
 int sr_set_option(sr_ctx *ctx, const char *name, int64_t value);
@@ -127,14 +128,15 @@ int sr_profile_reset(sr_ctx *ctx);
 /* Schedule facts for the current tree: number of pruning steps, stack depth needed, and the
  * algorithmic flops per column per rate class (820*E_int + 20*E_leaf + 1200). */
 int sr_schedule_info(sr_ctx *ctx, int64_t *n_steps, int32_t *stack_depth, double *flops_per_column_rate);
-/* Host-only (no GPU needed): the fused pruning schedule sr_set_tree would build. steps[8*i..] = {word, alignment row of
- * gather 0, 1, 2, second row of the step's first and second cherry gather, 0, 0}; word bits: 0-1 MV (1 = A=P·A,
+/* Host-only (no GPU needed): the fused pruning schedule sr_set_tree would build. steps[12*i..] = {word, alignment row of
+ * gather 0, 1, 2; second row of the step's first and second clade gather, their third rows; first table row of each, 0, 0};
+ * word bits: 0-1 MV (1 = A=P·A,
  * 2 = A=pop∘P·A), 2-3 number of tip gathers before the MV, 4 first gather starts a new partial, 5 one tip gather after
  * the MV, 6 rescale, 7 push, 8/9 store as root child A/B, 10-11 and 12-13 positions (1-based, among the step's gathers) of
- * up to two collapsed-cherry gathers, 14-31 index of the first one's table (the second uses the next).
+ * up to two collapsed-clade gathers, 14 / 15 the first / second of them is a pitchfork (three tips).
  * node_slot[v] = position of node v's parent edge in the matrix stream (per step: MV first, then tips), -1 if it has
- * none, -2-c if v is collapsed cherry c (an internal node whose two children are tips: with `cherry_tables` its
- * contribution to its parent is tabulated per state pair and gathered like a tip's).
+ * none, -2-c if v is the top of collapsed clade c (a cherry: two tip children; or a pitchfork: a cherry and a tip — with
+ * `cherry_tables` its contribution to its parent is tabulated per state combination and gathered like a tip's).
  * This replaces the recursion order of downTreeMarginal (JointBranchReconstruction.java:191-247). */
 int sr_schedule_dump(int32_t n_nodes, const int32_t *child_off, const int32_t *child_idx, const double *blen,
                      const int32_t *leaf_row, int32_t root, int32_t rescale_every, int32_t cherry_tables, int64_t cap_steps,
@@ -146,10 +148,11 @@ int sr_measure_fp64_peak(sr_ctx *ctx, double ms, double *tflops);
  * (parity hook for `model.getTransitionProbabilities`, JointBranchReconstruction.java:217);
  * node == root returns the merged root-branch matrix (:99). */
 int sr_debug_pmatrix(sr_ctx *ctx, int32_t node, int32_t rate_class, double out[400]);
-/* Copies the device-built table of a collapsed cherry (node = the cherry's internal node) to host:
- * out[(s_a*21 + s_b)*20 + i] = Σ_k P_node[i][k]·P_a[k][s_a]·P_b[k][s_b], states 0..19 and 20 = missing data
- * (parity hook for the three transition matrices and the inner loop of JointBranchReconstruction.java:208-230). */
-int sr_debug_cherry_table(sr_ctx *ctx, int32_t node, int32_t rate_class, double out[441 * 20]);
+/* Copies the device-built table of a collapsed clade (node = its top node) to host, 20 doubles per row; *n_rows = 441
+ * for a cherry (tips a, b): out[(s_a*21 + s_b)*20 + i] = Σ_k P_node[i][k]·P_a[k][s_a]·P_b[k][s_b]; 9261 for a pitchfork
+ * (cherry (a, b) and tip t below node): row (s_a*21 + s_b)*21 + s_t. States 0..19, 20 = missing data. Parity hook for the
+ * transition matrices and the inner loop of JointBranchReconstruction.java:208-230. */
+int sr_debug_cherry_table(sr_ctx *ctx, int32_t node, int32_t rate_class, double *out, int64_t cap_doubles, int32_t *n_rows);
 
 #ifdef __cplusplus
 }

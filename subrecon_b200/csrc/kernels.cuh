@@ -31,6 +31,7 @@ constexpr int FRAG_BYTES = FRAG_DOUBLES * 8;      // 4096
 constexpr int TABLE_DOUBLES = 21 * NS;            // P^T rows for states 0..19 + the missing-data row
 constexpr int TABLE_BYTES = TABLE_DOUBLES * 8;    // 3360
 constexpr int CHERRY_ROWS = 21 * 21;          // state pairs (s_a, s_b), 20 = missing
+constexpr int PITCHFORK_ROWS = 21 * 21 * 21;  // state triples (s_a, s_b, s_t)
 constexpr int CHERRY_ROW_DOUBLES = 24;        // 4 groups of 5 values + 1 pad: a lane fetches its group with three 16-byte loads
 
 // ------------------------------------------------------------------------------------------- PTX helpers
@@ -179,20 +180,24 @@ struct CherryParams {
     const double* evec;        // [400]
     const double* ievc;        // [400]
     const double* rates;       // [K]
-    const double* blen;        // [n_cherry][3] = {tip a, tip b, v}
-    double* ctab;              // [K][n_cherry][CHERRY_ROWS][CHERRY_ROW_DOUBLES]
-    int64_t rate_stride;
-    int n_cherry;
+    const double* blen;        // [n][5] = {tip a, tip b, top node, (pitchfork:) cherry edge, third tip}
+    const int32_t* kind;       // [n] 2 = cherry, 3 = pitchfork
+    const int64_t* rowoff;     // [n] first row inside one rate class's block
+    double* ctab;              // [K][rows][CHERRY_ROW_DOUBLES]
+    int64_t rate_stride;       // doubles per rate class
 };
 
+// Dynamic shared memory (pitchforks only): U[441][20], the absorbed cherry's vector per state pair.
 __global__ void __launch_bounds__(256) cherry_kernel(CherryParams p) {
     __shared__ double iexp[NS * NS];
-    __shared__ double Pm[3][NS * NS];
-    __shared__ double Tt[2][21 * NS];                  // Tt[m][s][k] = P_m[k][s]; s = 20: row sum of P_m
+    __shared__ double Pm[5][NS * NS];
+    __shared__ double Tt[3][21 * NS];                  // Tt[m][s][k] = P_m[k][s] for tips a, b, t; s = 20: row sum of P_m
+    extern __shared__ __align__(16) double U[];
     const int cid = blockIdx.x, kr = blockIdx.y, tid = threadIdx.x;
+    const int kind = p.kind[cid];
     const double rate = p.rates[kr];
-    for (int m = 0; m < 3; ++m) {
-        double t = p.blen[cid * 3 + m] * rate;
+    for (int m = 0; m < (kind == 3 ? 5 : 3); ++m) {
+        double t = p.blen[cid * 5 + m] * rate;
         if (t < 1e-9) t = 1e-9;
         __syncthreads();
         for (int e = tid; e < NS * NS; e += 256) iexp[e] = __dmul_rn(p.ievc[e], exp(__dmul_rn(t, p.eval[e / NS])));
@@ -206,30 +211,64 @@ __global__ void __launch_bounds__(256) cherry_kernel(CherryParams p) {
         }
     }
     __syncthreads();
-    for (int e = tid; e < 2 * 21 * NS; e += 256) {
+    // tip tables of a, b (matrices 0, 1) and, for a pitchfork, t (matrix 4)
+    for (int e = tid; e < 3 * 21 * NS; e += 256) {
         const int m = e / (21 * NS), sk = e % (21 * NS), st = sk / NS, k = sk % NS;
+        if (m == 2 && kind != 3) continue;
+        const double* P = Pm[m == 2 ? 4 : m];
         double v;
-        if (st < NS) v = Pm[m][k * NS + st];
+        if (st < NS) v = P[k * NS + st];
         else {
             double acc = 0.0;
-            for (int j = 0; j < NS; ++j) acc = __dadd_rn(acc, Pm[m][k * NS + j]);
+            for (int j = 0; j < NS; ++j) acc = __dadd_rn(acc, P[k * NS + j]);
             v = acc;
         }
         Tt[m][sk] = v;
     }
     __syncthreads();
-    double* out = p.ctab + (size_t)kr * p.rate_stride + (size_t)cid * CHERRY_ROWS * CHERRY_ROW_DOUBLES;
-    for (int e = tid; e < CHERRY_ROWS * CHERRY_ROW_DOUBLES; e += 256) {
+    double* out = p.ctab + (size_t)kr * p.rate_stride + (size_t)p.rowoff[cid] * CHERRY_ROW_DOUBLES;
+    if (kind == 2) {
+        for (int e = tid; e < CHERRY_ROWS * CHERRY_ROW_DOUBLES; e += 256) {
+            const int row = e / CHERRY_ROW_DOUBLES, col = e % CHERRY_ROW_DOUBLES, grp = col / 6, r = col % 6;
+            double v = 0.0;
+            if (r < 5) {
+                const int i = grp * 5 + r, sa = row / 21, sb = row % 21;
+                const double* ta = Tt[0] + sa * NS;
+                const double* tb = Tt[1] + sb * NS;
+                const double* pv = Pm[2] + i * NS;
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) s = __dadd_rn(s, __dmul_rn(pv[k], __dmul_rn(ta[k], tb[k])));
+                v = s;
+            }
+            out[e] = v;
+        }
+        return;
+    }
+    // pitchfork: first the absorbed cherry's vector up its own edge (matrix 3), per state pair ...
+    for (int e = tid; e < CHERRY_ROWS * NS; e += 256) {
+        const int row = e / NS, k = e % NS, sa = row / 21, sb = row % 21;
+        const double* ta = Tt[0] + sa * NS;
+        const double* tb = Tt[1] + sb * NS;
+        const double* pc = Pm[3] + k * NS;
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < NS; ++m) s = __dadd_rn(s, __dmul_rn(pc[m], __dmul_rn(ta[m], tb[m])));
+        U[e] = s;
+    }
+    __syncthreads();
+    // ... then the top node: (cherry vector x third tip) carried up the node's own edge (matrix 2)
+    for (int e = tid; e < PITCHFORK_ROWS * CHERRY_ROW_DOUBLES; e += 256) {
         const int row = e / CHERRY_ROW_DOUBLES, col = e % CHERRY_ROW_DOUBLES, grp = col / 6, r = col % 6;
         double v = 0.0;
         if (r < 5) {
-            const int i = grp * 5 + r, sa = row / 21, sb = row % 21;
-            const double* ta = Tt[0] + sa * NS;
-            const double* tb = Tt[1] + sb * NS;
+            const int i = grp * 5 + r, sab = row / 21, st = row % 21;
+            const double* u = U + sab * NS;
+            const double* tt = Tt[2] + st * NS;
             const double* pv = Pm[2] + i * NS;
             double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < NS; ++k) s = __dadd_rn(s, __dmul_rn(pv[k], __dmul_rn(ta[k], tb[k])));
+            for (int k = 0; k < NS; ++k) s = __dadd_rn(s, __dmul_rn(pv[k], __dmul_rn(u[k], tt[k])));
             v = s;
         }
         out[e] = v;
@@ -357,15 +396,17 @@ enum : int32_t {
     STF_STORE_A = 1 << 8,
     STF_STORE_B = 1 << 9,
     STF_ANY = STF_RESCALE | STF_PUSH | STF_STORE_A | STF_STORE_B,
-    ST_PSEUDO_SHIFT = 10,    // bits 10-11: 1-based position (among the step's gathers) of its first cherry-table gather, 0 = none
-    ST_PSEUDO2_SHIFT = 12,   // bits 12-13: position of a second one (0 = none); its table is the next one (index + 1)
-    ST_CHERRY_SHIFT = 14     // bits 14-31: index of the first cherry's table
+    ST_PSEUDO_SHIFT = 10,    // bits 10-11: 1-based position (among the step's gathers) of its first clade-table gather, 0 = none
+    ST_PSEUDO2_SHIFT = 12,   // bits 12-13: position of a second one (0 = none)
+    ST_PSEUDO_TRI = 1 << 14, // the first / second clade gather is a pitchfork (three state rows, 9261 table rows)
+    ST_PSEUDO2_TRI = 1 << 15
 };
-constexpr int STEP_INTS = 8;                  // {word, row of gather 0, 1, 2}, {second rows of the two cherry gathers, 0, 0}
+// {word, row of gather 0, 1, 2}, {second rows of the two clade gathers, their third rows}, {first table row of each, 0, 0}
+constexpr int STEP_INTS = 12;
 
 struct PruneParams {
-    const int4* steps;         // [n_steps][2] {word, row of gather 0, 1, 2}, {second row of the cherry gather, -, -, -}
-    const double* ctab;        // [K][n_cherry][CHERRY_ROWS][CHERRY_ROW_DOUBLES] cherry tables
+    const int4* steps;         // [n_steps][3], see STEP_INTS
+    const double* ctab;        // [K][ctab rows][CHERRY_ROW_DOUBLES] clade tables (cherries: 441 rows, pitchforks: 9261)
     int64_t ctab_rate_stride;  // doubles per rate class
     const int32_t* step_off;   // [n_steps] offset (doubles) of the step's matrices inside one rate class's stream
     const double* pstream;     // [K][rate_stride]
@@ -401,7 +442,7 @@ struct PruneCfg {
     static constexpr int LEVEL_DOUBLES = W * M * 5 * 32;
     static constexpr int LEVEL_BYTES = LEVEL_DOUBLES * 8;
     static constexpr int STATES_OFF = FRAG_BYTES + 3 * TABLE_BYTES;                 // 13920
-    static constexpr int STAGE_BYTES = ((STATES_OFF + 5 * S + 127) / 128) * 128;    // 3 gather rows + the second rows of up to two cherry gathers
+    static constexpr int STAGE_BYTES = ((STATES_OFF + 7 * S + 127) / 128) * 128;    // 3 gather rows + second and third rows of up to two clade gathers
 };
 
 __host__ __device__ constexpr int prune_bar_bytes(int nstage) { return ((2 * nstage * 8 + 127) / 128) * 128; }
@@ -471,7 +512,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
     uint32_t it = 0;                                  // ring position, runs on across work items
 
     // issue the TMA copies of one step (global ring position itp; work item `item_p`, step `step_p`) — one thread
-    auto issue_step = [&](uint32_t itp, int item_p, const int4 d, const int2 row_b, const int off_d, bool wait_empty) {
+    auto issue_step = [&](uint32_t itp, int item_p, const int4 d, const int4 row_x, const int off_d, bool wait_empty) {
         const int kp = item_p / p.n_tiles, tilep = item_p - kp * p.n_tiles;
         const double* ps = p.pstream + (size_t)kp * p.rate_stride;
         const uint8_t* st = p.states + p.col0 + (int64_t)tilep * S;
@@ -480,12 +521,15 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
         const int n_leaf = ((d.x >> ST_NPRE_SHIFT) & 3) + ((d.x & ST_NPOST) ? 1 : 0);
         // a cherry gather brings a second state row and no table
         const int pseudo = (((d.x >> ST_PSEUDO_SHIFT) & 3) ? 1 : 0) + (((d.x >> ST_PSEUDO2_SHIFT) & 3) ? 1 : 0);
+        const int tri1 = (d.x & ST_PSEUDO_TRI) ? 1 : 0, tri2 = (d.x & ST_PSEUDO2_TRI) ? 1 : 0;
         const uint32_t pbytes = ((d.x & ST_MV_MASK) ? FRAG_BYTES : 0) + (n_leaf - pseudo) * TABLE_BYTES;
         if (wait_empty) mbar_wait(&empty[stage], ph ^ 1);
         unsigned char* dst = stages + stage * STAGE_BYTES;
-        mbar_expect_tx(&full[stage], pbytes + (n_leaf + pseudo) * S);
-        if (pseudo > 0) bulk_g2s(dst + Cfg::STATES_OFF + 3 * S, st + (int64_t)row_b.x * p.pitch, S, &full[stage]);
-        if (pseudo > 1) bulk_g2s(dst + Cfg::STATES_OFF + 4 * S, st + (int64_t)row_b.y * p.pitch, S, &full[stage]);
+        mbar_expect_tx(&full[stage], pbytes + (n_leaf + pseudo + tri1 + tri2) * S);
+        if (pseudo > 0) bulk_g2s(dst + Cfg::STATES_OFF + 3 * S, st + (int64_t)row_x.x * p.pitch, S, &full[stage]);
+        if (pseudo > 1) bulk_g2s(dst + Cfg::STATES_OFF + 4 * S, st + (int64_t)row_x.y * p.pitch, S, &full[stage]);
+        if (tri1) bulk_g2s(dst + Cfg::STATES_OFF + 5 * S, st + (int64_t)row_x.z * p.pitch, S, &full[stage]);
+        if (tri2) bulk_g2s(dst + Cfg::STATES_OFF + 6 * S, st + (int64_t)row_x.w * p.pitch, S, &full[stage]);
         if (pbytes) bulk_g2s(dst, ps + off_d, pbytes, &full[stage]);
         if (n_leaf > 0) bulk_g2s(dst + Cfg::STATES_OFF, st + (int64_t)d.y * p.pitch, S, &full[stage]);
         if (n_leaf > 1) bulk_g2s(dst + Cfg::STATES_OFF + S, st + (int64_t)d.z * p.pitch, S, &full[stage]);
@@ -497,7 +541,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
         if (lane == 0) {
             for (int item = blockIdx.x; item < n_items; item += gridDim.x)
                 for (int step = 0; step < p.n_steps; ++step, ++it)
-                    issue_step(it, item, __ldg(p.steps + 2 * step), __ldg(reinterpret_cast<const int2*>(p.steps + 2 * step + 1)), __ldg(p.step_off + step), true);
+                    issue_step(it, item, __ldg(p.steps + 3 * step), __ldg(p.steps + 3 * step + 1), __ldg(p.step_off + step), true);
         }
     };
     if (RA) {
@@ -531,10 +575,10 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
     int my_item = blockIdx.x, my_step = warp;
     int4 my_d = make_int4(0, 0, 0, 0);
     int my_off = 0;
-    int2 my_rowb = make_int2(0, 0);
+    int4 my_rowb = make_int4(0, 0, 0, 0);
     auto my_normalise = [&]() {
         while (my_item < n_items && my_step >= p.n_steps) { my_step -= p.n_steps; my_item += gridDim.x; }
-        if (my_item < n_items) { my_d = __ldg(p.steps + 2 * my_step); my_rowb = __ldg(reinterpret_cast<const int2*>(p.steps + 2 * my_step + 1)); my_off = __ldg(p.step_off + my_step); }
+        if (my_item < n_items) { my_d = __ldg(p.steps + 3 * my_step); my_rowb = __ldg(p.steps + 3 * my_step + 1); my_off = __ldg(p.step_off + my_step); }
     };
     // try (or, if `block`, wait) to refill my next position; returns after at most one refill
     auto my_refill = [&](bool block) {
@@ -574,6 +618,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
         }
         int sp = 0;
         int w_next = __ldg(&p.steps[0].x);
+        int2 ro_next = __ldg(reinterpret_cast<const int2*>(p.steps + 2));     // first table rows of the step's clade gathers
         bool next_ready = false;           // result of an early, non-blocking probe of a later stage's full barrier
         // HOLES encodes before which k-steps (1..4) the burst pauses: 0 none, 1 -> {3}, 2 -> {2,4}, digits "ab.." -> {a,b,..}
         constexpr int HMASK = hole_mask(HOLES);
@@ -597,7 +642,8 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
             const uint32_t ph = (it / NSTAGE) & 1;
             const int w = w_next;
             const bool has_next = step + 1 < p.n_steps;
-            if (has_next) w_next = __ldg(&p.steps[2 * (step + 1)].x);
+            const int2 ro = ro_next;
+            if (has_next) { w_next = __ldg(&p.steps[3 * (step + 1)].x); ro_next = __ldg(reinterpret_cast<const int2*>(p.steps + 3 * (step + 1) + 2)); }
             SR_TL(0);                                   // step begins
             if (INL) my_refill(/*block=*/my_pos <= it);
             const int mv = w & ST_MV_MASK, n_pre = (w >> ST_NPRE_SHIFT) & 3;
@@ -655,19 +701,20 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
             const double* crow[M];
             const double* crow2[TWOPS ? M : 1];
             if (ps) {
-                const unsigned cid = (unsigned)w >> ST_CHERRY_SHIFT;
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
                     const int sa = ps == 1 ? s0[j] : (ps == 2 ? s1[j] : s2[j]);
-                    const int sb = stb[3 * S + j * 8];
-                    crow[j] = ctab_k + ((size_t)cid * CHERRY_ROWS + sa * 21 + sb) * CHERRY_ROW_DOUBLES;
+                    int ix = sa * 21 + stb[3 * S + j * 8];
+                    if (w & ST_PSEUDO_TRI) ix = ix * 21 + stb[5 * S + j * 8];
+                    crow[j] = ctab_k + ((size_t)ro.x + ix) * CHERRY_ROW_DOUBLES;
                 }
                 if (TWOPS && ps2) {
 #pragma unroll
                     for (int j = 0; j < M; ++j) {
                         const int sa = ps2 == 2 ? s1[j] : s2[j];
-                        const int sb = stb[4 * S + j * 8];
-                        crow2[TWOPS ? j : 0] = ctab_k + ((size_t)(cid + 1) * CHERRY_ROWS + sa * 21 + sb) * CHERRY_ROW_DOUBLES;
+                        int ix = sa * 21 + stb[4 * S + j * 8];
+                        if (w & ST_PSEUDO2_TRI) ix = ix * 21 + stb[6 * S + j * 8];
+                        crow2[TWOPS ? j : 0] = ctab_k + ((size_t)ro.y + ix) * CHERRY_ROW_DOUBLES;
                     }
                 }
             }

@@ -69,9 +69,13 @@ struct sr_ctx {
     double root_blen = 0.0;
     bool sched_dirty = true, p_dirty = true;
     // collapsed cherries (an internal node whose two children are tips, not a root child): node, tip rows, edge lengths
-    std::vector<int32_t> cherry_node;
-    std::vector<double> cherry_blen;             // [n_cherry][3] = {tip a, tip b, the node's own edge}
-    DevBuf d_ctab, d_cherry_blen;
+    // clade tables, in the order the schedule uses them: a cherry (node, tips a b) or a pitchfork (node, cherry a b, tip t)
+    std::vector<int32_t> cherry_node;            // the clade's top node
+    std::vector<int32_t> cherry_kind;            // 2 = cherry (441 rows), 3 = pitchfork (9261 rows)
+    std::vector<int64_t> cherry_rowoff;          // first row of the table inside one rate class's block
+    std::vector<double> cherry_blen;             // [n][5] = {tip a, tip b, the node's own edge, (pitchfork:) cherry edge, third tip}
+    int64_t ctab_rows = 0;                       // rows per rate class
+    DevBuf d_ctab, d_cherry_blen, d_cherry_meta;
 #ifdef SR_TIMELINE
     DevBuf d_timeline;
 #endif
@@ -82,8 +86,9 @@ struct sr_ctx {
     int holes = 2;                      // pauses inside a warp's MMA burst (0..2), see kernels.cuh
     int cherry_pairs = 1;               // let one step gather two cherries (siblings): trees with many cherry pairs
     bool has_pairs = false;             // the current schedule contains such steps (selects the kernel variant)
+    int cherry_pitchforks = 1;          // also tabulate (cherry, tip) clades: 9261 rows each
     int cherry_tables = 1;              // collapse cherries into 441-row lookup tables (see build_schedule)
-    int64_t cherry_table_mb = 1024;     // memory cap for those tables; cherries beyond it are pruned the ordinary way
+    int64_t cherry_table_mb = 4096;     // memory cap for those tables; clades beyond it are pruned the ordinary way
     bool input_chars = false;           // alignment bytes are residue letters, translated on the device
     int compress = 0;                   // reduce every batch to its distinct column patterns first
     int prefetch = 0;                   // fetch the next step's first operands inside the current MMA burst
@@ -166,18 +171,29 @@ int build_schedule(sr_ctx* c) {
     // (s_a, s_b): 21 x 21 possibilities. K1 tabulates u for all of them once per rate class (CHERRY_ROWS x 20 doubles), and
     // the pruning kernel treats v as a tip with 441 states: two gathers and one 20x20 contraction per column become one
     // gather. A Yule tree has ~N/3 cherries, a balanced one N/2, so a third to a half of all contractions disappear.
-    std::vector<int32_t> cherry_of(n, -1);
-    c->cherry_node.clear(); c->cherry_blen.clear();
+    // Pitchforks: a node whose children are a collapsed cherry (a, b) and a tip t gets the same treatment one level up —
+    // 21^3 state triples, 9261 rows — and absorbs the cherry: another contraction and another gather per column gone.
+    std::vector<int32_t> cherry_of(n, -1);       // 2 / 3 = collapsed cherry / pitchfork (replaced by the table index below)
+    c->cherry_node.clear(); c->cherry_kind.clear(); c->cherry_rowoff.clear(); c->cherry_blen.clear();
+    c->ctab_rows = 0;
     if (c->cherry_tables && !c->prefetch) {
-        const int64_t per = (int64_t)std::max(1, c->K) * CHERRY_ROWS * CHERRY_ROW_DOUBLES * (int64_t)sizeof(double);
-        const int64_t cap = std::min<int64_t>((c->cherry_table_mb << 20) / per, (1 << 18) - 2);
-        for (int v = 0; v < n && (int64_t)c->cherry_node.size() < cap; ++v) {
+        const int64_t row_bytes = (int64_t)std::max(1, c->K) * CHERRY_ROW_DOUBLES * (int64_t)sizeof(double);
+        int64_t rows_left = (c->cherry_table_mb << 20) / row_bytes;
+        int n_tab = 0;
+        const int max_tab = 1 << 20;
+        for (int v = 0; v < n && rows_left >= CHERRY_ROWS && n_tab < max_tab; ++v) {
             if (v == c->root || v == rc0 || v == rc1 || off[v + 1] - off[v] != 2) continue;
-            const int a = idx[off[v]], b = idx[off[v] + 1];
-            if (!is_leaf(a) || !is_leaf(b)) continue;
-            cherry_of[v] = (int32_t)c->cherry_node.size();
-            c->cherry_node.push_back(v);
-            c->cherry_blen.push_back(c->blen[a]); c->cherry_blen.push_back(c->blen[b]); c->cherry_blen.push_back(c->blen[v]);
+            if (!is_leaf(idx[off[v]]) || !is_leaf(idx[off[v] + 1])) continue;
+            cherry_of[v] = 2; rows_left -= CHERRY_ROWS; ++n_tab;
+        }
+        if (c->cherry_pitchforks) {
+            for (int v = 0; v < n && rows_left >= PITCHFORK_ROWS - CHERRY_ROWS; ++v) {
+                if (v == c->root || v == rc0 || v == rc1 || off[v + 1] - off[v] != 2) continue;
+                const int x = idx[off[v]], y = idx[off[v] + 1];
+                const int ch = cherry_of[x] == 2 ? x : (cherry_of[y] == 2 ? y : -1);
+                if (ch < 0 || !is_leaf(ch == x ? y : x)) continue;
+                cherry_of[v] = 3; cherry_of[ch] = -1; rows_left -= PITCHFORK_ROWS - CHERRY_ROWS;
+            }
         }
     }
     auto is_tip = [&](int v) { return is_leaf(v) || cherry_of[v] >= 0; };
@@ -234,21 +250,26 @@ int build_schedule(sr_ctx* c) {
         (which == 0 ? prims.back().store_a : prims.back().store_b) = true;
     }
 
-    // cherry tables are numbered in the order the schedule uses them, so that two cherry gathers of one step have
-    // consecutive indices (the step word carries only the first)
-    {
-        std::vector<int32_t> nodes;
-        std::vector<double> lens;
-        for (const Prim& pr : prims) {
-            if (pr.code > P_LEAF_MUL || cherry_of[pr.child] < 0) continue;
-            const int old_id = cherry_of[pr.child];
-            cherry_of[pr.child] = (int32_t)nodes.size();
-            nodes.push_back(pr.child);
-            for (int t = 0; t < 3; ++t) lens.push_back(c->cherry_blen[3 * old_id + t]);
+    // clade tables are laid out in the order the schedule uses them
+    for (const Prim& pr : prims) {
+        if (pr.code > P_LEAF_MUL || cherry_of[pr.child] < 0) continue;
+        const int v = pr.child, kind = cherry_of[v];
+        int a, b, t = -1, ce = -1;
+        if (kind == 2) { a = idx[off[v]]; b = idx[off[v] + 1]; }
+        else {
+            const int x = idx[off[v]], y = idx[off[v] + 1];
+            ce = is_leaf(x) ? y : x; t = is_leaf(x) ? x : y;
+            a = idx[off[ce]]; b = idx[off[ce] + 1];
         }
-        c->cherry_node.swap(nodes);
-        c->cherry_blen.swap(lens);
+        cherry_of[v] = (int32_t)c->cherry_node.size();
+        c->cherry_node.push_back(v);
+        c->cherry_kind.push_back(kind);
+        c->cherry_rowoff.push_back(c->ctab_rows);
+        c->ctab_rows += kind == 2 ? CHERRY_ROWS : PITCHFORK_ROWS;
+        const double lens[5] = {c->blen[a], c->blen[b], c->blen[v], ce >= 0 ? c->blen[ce] : 0.0, t >= 0 ? c->blen[t] : 0.0};
+        c->cherry_blen.insert(c->cherry_blen.end(), lens, lens + 5);
     }
+    if (c->ctab_rows > INT32_MAX) return fail(c, SR_ERR_UNSUPPORTED, "clade tables too large for 32-bit row offsets; lower cherry_table_mb");
     // (two cherry gathers per step only for the default kernel layout: the tuning variants are single-gather builds)
     const bool default_layout = c->tile_m == 2 && c->warps == 12 && c->realloc && !c->prefetch && c->holes == 2;
     const int max_pseudo = (c->cherry_pairs && default_layout) ? 2 : 1;
@@ -263,12 +284,23 @@ int build_schedule(sr_ctx* c) {
     int s_cur = 0;                               // edges multiplied into A since its last rescale
     std::vector<int> s_stack;
     int64_t off_d = 0;
+    // alignment rows of a collapsed clade's tips in table-index order (a, b[, t]); returns their number
+    auto clade_rows = [&](int v, int (&rws)[3]) {
+        const int kind = c->cherry_kind[cherry_of[v]];
+        if (kind == 2) { rws[0] = c->leaf_row[idx[off[v]]]; rws[1] = c->leaf_row[idx[off[v] + 1]]; rws[2] = 0; return 2; }
+        const int x = idx[off[v]], y = idx[off[v] + 1];
+        const int ce = is_leaf(x) ? y : x, t = is_leaf(x) ? x : y;
+        rws[0] = c->leaf_row[idx[off[ce]]]; rws[1] = c->leaf_row[idx[off[ce] + 1]]; rws[2] = c->leaf_row[t];
+        return 3;
+    };
     auto add_slot = [&](const Prim& pr) {
         if (cherry_of[pr.child] >= 0) {          // no matrices in the stream: the table lives in its own buffer
-            const int a = idx[off[pr.child]], b = idx[off[pr.child] + 1];
-            c->node_slot[pr.child] = -2 - cherry_of[pr.child];
-            c->e_leaf += 2; ++c->e_int;          // the algorithmic work it stands for is unchanged
-            c->max_leaf_row = std::max(c->max_leaf_row, std::max(c->leaf_row[a], c->leaf_row[b]));
+            const int tid = cherry_of[pr.child];
+            int rws[3];
+            const int nr = clade_rows(pr.child, rws);
+            c->node_slot[pr.child] = -2 - tid;
+            c->e_leaf += nr; c->e_int += nr - 1;  // the algorithmic work it stands for is unchanged
+            for (int t = 0; t < nr; ++t) c->max_leaf_row = std::max(c->max_leaf_row, rws[t]);
             return;
         }
         const bool leaf = pr.code <= P_LEAF_MUL;
@@ -282,19 +314,22 @@ int build_schedule(sr_ctx* c) {
     };
     size_t i = 0;
     while (i < prims.size()) {
-        int32_t word = 0, rows[3] = {0, 0, 0}, row_b[2] = {0, 0};
+        int32_t word = 0, rows[3] = {0, 0, 0}, row_b[2] = {0, 0}, row_c[2] = {0, 0}, row_off[2] = {0, 0};
         int n_leaf = 0, n_pre = 0;
         int n_pseudo = 0;                        // cherry-table gathers of this step (at most max_pseudo)
         auto is_pseudo = [&](const Prim& pr) { return pr.code <= P_LEAF_MUL && cherry_of[pr.child] >= 0; };
         auto take_gather = [&](const Prim& pr) {
             if (is_pseudo(pr)) {
-                const int a = idx[off[pr.child]], b = idx[off[pr.child] + 1];
-                rows[n_leaf++] = c->leaf_row[a];
-                row_b[n_pseudo] = c->leaf_row[b];
-                if (n_pseudo == 0) word |= (n_leaf << ST_PSEUDO_SHIFT) | (cherry_of[pr.child] << ST_CHERRY_SHIFT);
-                else word |= n_leaf << ST_PSEUDO2_SHIFT;
+                int rws[3];
+                const int nr = clade_rows(pr.child, rws);
+                rows[n_leaf++] = rws[0];
+                row_b[n_pseudo] = rws[1];
+                row_c[n_pseudo] = rws[2];
+                row_off[n_pseudo] = (int32_t)c->cherry_rowoff[cherry_of[pr.child]];
+                word |= n_leaf << (n_pseudo == 0 ? ST_PSEUDO_SHIFT : ST_PSEUDO2_SHIFT);
+                if (nr == 3) word |= (n_pseudo == 0 ? ST_PSEUDO_TRI : ST_PSEUDO2_TRI);
                 ++n_pseudo;
-                ++s_cur;                         // two edges deep
+                s_cur += nr - 1;                 // two or three edges deep
             } else {
                 rows[n_leaf++] = c->leaf_row[pr.child];
             }
@@ -349,7 +384,8 @@ int build_schedule(sr_ctx* c) {
         if (last->store_b) word |= STF_STORE_B;
         c->steps.push_back(word);
         c->steps.push_back(rows[0]); c->steps.push_back(rows[1]); c->steps.push_back(rows[2]);
-        c->steps.push_back(row_b[0]); c->steps.push_back(row_b[1]); c->steps.push_back(0); c->steps.push_back(0);
+        c->steps.push_back(row_b[0]); c->steps.push_back(row_b[1]); c->steps.push_back(row_c[0]); c->steps.push_back(row_c[1]);
+        c->steps.push_back(row_off[0]); c->steps.push_back(row_off[1]); c->steps.push_back(0); c->steps.push_back(0);
         if (n_pseudo > 1) c->has_pairs = true;
         if (off_d > INT32_MAX - 4096) return fail(c, SR_ERR_UNSUPPORTED, "tree too large for 32-bit matrix-stream offsets");
     }
@@ -423,19 +459,27 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     CUDA_TRY(c, cudaGetLastError());
     const int n_cherry = (int)c->cherry_node.size();
     if (n_cherry > 0) {
-        const int64_t stride = (int64_t)n_cherry * CHERRY_ROWS * CHERRY_ROW_DOUBLES;
+        const int64_t stride = c->ctab_rows * CHERRY_ROW_DOUBLES;
         CUDA_TRY(c, c->d_ctab.reserve(sizeof(double) * (size_t)c->K * stride));
-        CUDA_TRY(c, c->d_cherry_blen.reserve(sizeof(double) * 3 * n_cherry));
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_cherry_blen.p, c->cherry_blen.data(), sizeof(double) * 3 * n_cherry, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, c->d_cherry_blen.reserve(sizeof(double) * 5 * n_cherry));
+        CUDA_TRY(c, c->d_cherry_meta.reserve((sizeof(int64_t) + sizeof(int32_t)) * (size_t)n_cherry + 16));
+        int64_t* d_rowoff = c->d_cherry_meta.as<int64_t>();
+        int32_t* d_kind = reinterpret_cast<int32_t*>(d_rowoff + n_cherry);
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_cherry_blen.p, c->cherry_blen.data(), sizeof(double) * 5 * n_cherry, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(d_rowoff, c->cherry_rowoff.data(), sizeof(int64_t) * n_cherry, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(d_kind, c->cherry_kind.data(), sizeof(int32_t) * n_cherry, cudaMemcpyHostToDevice, s));
         CherryParams cp{};
         cp.eval = pp.eval; cp.evec = pp.evec; cp.ievc = pp.ievc; cp.rates = pp.rates;
         cp.blen = c->d_cherry_blen.as<double>();
+        cp.kind = d_kind;
+        cp.rowoff = d_rowoff;
         cp.ctab = c->d_ctab.as<double>();
         cp.rate_stride = stride;
-        cp.n_cherry = n_cherry;
-        cherry_kernel<<<dim3(n_cherry, c->K), 256, 0, s>>>(cp);
+        const int usm = CHERRY_ROWS * NS * (int)sizeof(double);              // the pitchforks' scratch (70.6 KB)
+        CUDA_TRY(c, cudaFuncSetAttribute(cherry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, usm));
+        cherry_kernel<<<dim3(n_cherry, c->K), 256, usm, s>>>(cp);
         CUDA_TRY(c, cudaGetLastError());
-        CUDA_TRY(c, cudaStreamSynchronize(s));       // cherry_blen staging is host memory owned by the context; keep it simple
+        CUDA_TRY(c, cudaStreamSynchronize(s));       // the staging arrays are host memory owned by the context; keep it simple
     }
     c->p_dirty = false;
     return SR_OK;
@@ -484,7 +528,7 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     p.step_off = c->d_stepoff.as<int32_t>();
     p.pstream = c->d_pstream.as<double>();
     p.ctab = c->d_ctab.as<double>();
-    p.ctab_rate_stride = (int64_t)c->cherry_node.size() * CHERRY_ROWS * CHERRY_ROW_DOUBLES;
+    p.ctab_rate_stride = c->ctab_rows * CHERRY_ROW_DOUBLES;
     p.rate_stride = c->rate_stride;
     p.states = d_states;
     p.pitch = pitch;
@@ -999,6 +1043,9 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     } else if (k == "cherry_tables") {
         c->cherry_tables = value != 0;
         c->sched_dirty = true;
+    } else if (k == "cherry_pitchforks") {
+        c->cherry_pitchforks = value != 0;
+        c->sched_dirty = true;
     } else if (k == "cherry_pairs") {
         c->cherry_pairs = value != 0;
         c->sched_dirty = true;
@@ -1159,21 +1206,24 @@ int sr_debug_pmatrix(sr_ctx* c, int32_t node, int32_t k, double* out) {
     return SR_OK;
 }
 
-int sr_debug_cherry_table(sr_ctx* c, int32_t node, int32_t k, double* out) {
+int sr_debug_cherry_table(sr_ctx* c, int32_t node, int32_t k, double* out, int64_t cap_doubles, int32_t* n_rows) {
     if (!c || !out) return SR_ERR_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc = ensure_pstream(c, c->stream);
     if (rc) return rc;
     if (k < 0 || k >= c->K || node < 0 || node >= c->n_nodes) return fail(c, SR_ERR_ARG, "node or rate class out of range");
-    if (c->node_slot[node] > -2) return fail(c, SR_ERR_ARG, "node %d is not a collapsed cherry", node);
+    if (c->node_slot[node] > -2) return fail(c, SR_ERR_ARG, "node %d is not a collapsed clade", node);
     const int cid = -2 - c->node_slot[node];
-    std::vector<double> buf((size_t)CHERRY_ROWS * CHERRY_ROW_DOUBLES);
-    const int64_t stride = (int64_t)c->cherry_node.size() * CHERRY_ROWS * CHERRY_ROW_DOUBLES;
-    CUDA_TRY(c, cudaMemcpyAsync(buf.data(), c->d_ctab.as<double>() + (size_t)k * stride + (size_t)cid * CHERRY_ROWS * CHERRY_ROW_DOUBLES,
+    const int rows = c->cherry_kind[cid] == 2 ? CHERRY_ROWS : PITCHFORK_ROWS;
+    if (n_rows) *n_rows = rows;
+    if (cap_doubles < (int64_t)rows * 20) return fail(c, SR_ERR_ARG, "output buffer too small: %d rows of 20 doubles", rows);
+    std::vector<double> buf((size_t)rows * CHERRY_ROW_DOUBLES);
+    const int64_t stride = c->ctab_rows * CHERRY_ROW_DOUBLES;
+    CUDA_TRY(c, cudaMemcpyAsync(buf.data(), c->d_ctab.as<double>() + (size_t)k * stride + (size_t)c->cherry_rowoff[cid] * CHERRY_ROW_DOUBLES,
                                 sizeof(double) * buf.size(), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    for (int row = 0; row < CHERRY_ROWS; ++row)
-        for (int i = 0; i < 20; ++i) out[row * 20 + i] = buf[(size_t)row * CHERRY_ROW_DOUBLES + (i / 5) * 6 + i % 5];
+    for (int row = 0; row < rows; ++row)
+        for (int i = 0; i < 20; ++i) out[(size_t)row * 20 + i] = buf[(size_t)row * CHERRY_ROW_DOUBLES + (i / 5) * 6 + i % 5];
     return SR_OK;
 }
 

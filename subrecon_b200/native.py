@@ -97,7 +97,7 @@ def lib():
                                        ctypes.POINTER(ctypes.c_double)]
         L.sr_measure_fp64_peak.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
         L.sr_debug_pmatrix.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, _D]
-        L.sr_debug_cherry_table.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, _D]
+        L.sr_debug_cherry_table.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, _D, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
         L.sr_schedule_dump.argtypes = [ctypes.c_int32, _I32, _I32, _D, _I32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                        ctypes.c_int64, _I32, _I32, ctypes.POINTER(ctypes.c_int64),
                                        ctypes.POINTER(ctypes.c_int32)]
@@ -105,12 +105,13 @@ def lib():
     return _lib
 
 
-STEP_INTS = 8
+STEP_INTS = 12
 
 
 def schedule_dump(ft, rescale_every=8, cherry_tables=True):
-    """Host-only: the fused pruning schedule for a FlatTree -> (steps[n,8] int32, node_slot[n_nodes], stack_depth).
-    Step columns: word, alignment rows of gathers 0..2, second row of the step's cherry gather, 3 unused."""
+    """Host-only: the fused pruning schedule for a FlatTree -> (steps[n,12] int32, node_slot[n_nodes], stack_depth).
+    Step columns: word, alignment rows of gathers 0..2; second rows of the step's two clade gathers, their third rows;
+    first table row of each, 2 unused (include/subrecon_b200.h::sr_schedule_dump)."""
     off = np.ascontiguousarray(ft.child_off, dtype=np.int32)
     idx = np.ascontiguousarray(ft.child_idx, dtype=np.int32)
     bl = np.ascontiguousarray(ft.blen, dtype=np.float64)
@@ -269,7 +270,9 @@ class Context:
         return out
 
     def debug_cherry_table(self, node, rate_class):
-        """[21, 21, 20]: the vector collapsed cherry `node` hands to its parent, per state pair of its two tips."""
-        out = np.zeros((21, 21, 20))
-        self._ck(lib().sr_debug_cherry_table(self._h, int(node), int(rate_class), out.ctypes.data_as(_D)))
-        return out
+        """The vector collapsed clade `node` hands to its parent per state combination of its tips:
+        [21, 21, 20] for a cherry, [21, 21, 21, 20] for a pitchfork (cherry tips first, then the third tip)."""
+        out = np.zeros(21 * 21 * 21 * 20)
+        n = ctypes.c_int32()
+        self._ck(lib().sr_debug_cherry_table(self._h, int(node), int(rate_class), out.ctypes.data_as(_D), out.size, ctypes.byref(n)))
+        return out[:n.value * 20].reshape((21, 21, 20) if n.value == 441 else (21, 21, 21, 20))

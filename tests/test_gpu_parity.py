@@ -102,34 +102,54 @@ def _check_matrices(ctx, p):
 
 
 def test_cherry_tables_match_pal(ctx, example_problem):
-    """K1b: the table of a collapsed cherry against the reference's own arithmetic for that clade
-    (JointBranchReconstruction.java:208-230 with PAL's matrices): all 21 x 21 state pairs, missing data included."""
+    """K1b: the table of a collapsed clade against the reference's own arithmetic for that clade
+    (JointBranchReconstruction.java:208-230 with PAL's matrices): all 21 x 21 (x 21) state combinations, missing data
+    included — cherries and pitchforks."""
     p = example_problem
     setup(ctx, p)
-    _, node_slot, _ = native.schedule_dump(p.flat)
-    cherries = [v for v, s in enumerate(node_slot) if s <= -2]
-    assert len(cherries) >= 4
-    worst = 0.0
-    for v in cherries:
-        a, b = p.flat.child_idx[p.flat.child_off[v]:p.flat.child_off[v + 1]]
+    ft = p.flat
+    _, node_slot, _ = native.schedule_dump(ft)
+    clades = [v for v, s in enumerate(node_slot) if s <= -2]
+
+    def kids(v):
+        return list(ft.child_idx[ft.child_off[v]:ft.child_off[v + 1]])
+
+    def leaf(v):
+        return ft.child_off[v] == ft.child_off[v + 1]
+    worst, kinds = 0.0, set()
+    for v in clades:
         with pytest.raises(native.SrError):
             ctx.debug_pmatrix(v, 0)                                       # its matrices are not in the stream any more
         for k in (0, len(p.rates) - 1):
-            Pv, Pa, Pb = (oracle.transition_probs(p.model.Eval, p.model.Evec, p.model.Ievc, p.flat.blen[x] * p.rates[k]) for x in (v, a, b))
-            Ta = np.concatenate([Pa.T, Pa.sum(axis=1)[None, :]])          # [state or missing][k]
-            Tb = np.concatenate([Pb.T, Pb.sum(axis=1)[None, :]])
-            want = np.einsum("ik,ak,bk->abi", Pv, Ta, Tb)
+            def P(x):
+                return oracle.transition_probs(p.model.Eval, p.model.Evec, p.model.Ievc, ft.blen[x] * p.rates[k])
+
+            def T(x):                                                     # [state or missing][k]
+                return np.concatenate([P(x).T, P(x).sum(axis=1)[None, :]])
             got = ctx.debug_cherry_table(v, k)
+            if all(leaf(x) for x in kids(v)):
+                a, b = kids(v)
+                want = np.einsum("ik,ak,bk->abi", P(v), T(a), T(b))
+            else:
+                ce = [x for x in kids(v) if not leaf(x)][0]
+                t = [x for x in kids(v) if leaf(x)][0]
+                a, b = kids(ce)
+                u = np.einsum("km,am,bm->abk", P(ce), T(a), T(b))
+                want = np.einsum("ik,abk,tk->abti", P(v), u, T(t))
+            assert got.shape == want.shape
+            kinds.add(got.ndim)
             worst = max(worst, float(np.max(np.abs(got - want) / want)))
-    assert worst < 1e-9
-    # and the two ways of pruning agree far inside the tolerance
+    assert worst < 1e-9 and kinds == {3, 4}
+    # and the ways of pruning agree far inside the tolerance
     with_tables = ctx.run()
     try:
-        ctx.set_option("cherry_tables", 0)
-        without = ctx.run()
+        for opt in ("cherry_pitchforks", "cherry_tables"):
+            ctx.set_option(opt, 0)
+            without = ctx.run()
+            assert rel_err(with_tables["lnl"], without["lnl"]) < 1e-12 and rel_err(with_tables["joint"], without["joint"]) < 1e-10
     finally:
         ctx.set_option("cherry_tables", 1)
-    assert rel_err(with_tables["lnl"], without["lnl"]) < 1e-12 and rel_err(with_tables["joint"], without["joint"]) < 1e-10
+        ctx.set_option("cherry_pitchforks", 1)
 
 
 @pytest.mark.parametrize("tile_m", [2, 4])
@@ -225,7 +245,7 @@ def test_cfg5_subset(ctx):
                                   dict(warps=8, rotate=0), dict(holes=0), dict(holes=1), dict(holes=13), dict(holes=1234), dict(rotate=0),
                                   dict(warps=11), dict(warps=11, rotate=0), dict(warps=11, holes=0), dict(warps=11, holes=0, rotate=0),
                                   dict(warps=11, prefetch=1), dict(warps=11, prefetch=1, rotate=0), dict(warps=12), dict(warps=12, rotate=0),
-                                  dict(cherry_tables=0), dict(cherry_tables=0, warps=11), dict(cherry_tables=0, tile_m=4), dict(cherry_table_mb=1), dict(cherry_pairs=0),
+                                  dict(cherry_tables=0), dict(cherry_tables=0, warps=11), dict(cherry_tables=0, tile_m=4), dict(cherry_table_mb=1), dict(cherry_table_mb=40), dict(cherry_pairs=0), dict(cherry_pitchforks=0), dict(cherry_pitchforks=0, cherry_pairs=0),
                                   dict(cherry_pairs=0, rotate=0)])
 def test_kernel_variants_agree(ctx, opts):
     """Every tuning variant of the pruning kernel (sr_set_option) gives oracle-exact results."""
@@ -238,7 +258,7 @@ def test_kernel_variants_agree(ctx, opts):
         r = ctx.run()
         assert rel_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
     finally:
-        for k, v in dict(tile_m=2, holes=2, rotate=1, prefetch=0, cherry_tables=1, cherry_table_mb=1024, cherry_pairs=1).items():   # tile_m=2 restores the default warp layout
+        for k, v in dict(tile_m=2, holes=2, rotate=1, prefetch=0, cherry_tables=1, cherry_table_mb=4096, cherry_pairs=1, cherry_pitchforks=1).items():   # tile_m=2 restores the default warp layout
             ctx.set_option(k, v)
 
 

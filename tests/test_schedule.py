@@ -22,11 +22,28 @@ def run_schedule(p, cols, rescale_every=8, cherry_tables=True):
     assert sorted(slot_node) == list(range(len(slot_node)))                    # every edge exactly once, densely numbered
     assert sorted(cherry_node) == list(range(len(cherry_node))) and (cherry_tables or not cherry_node)
     rc = ft.child_idx[ft.child_off[ft.root]:ft.child_off[ft.root + 1]]
-    # every non-root edge is either in the matrix stream or inside a cherry table (3 edges each)
-    assert len(slot_node) + 3 * len(cherry_node) == ft.n_nodes - 1 - sum(1 for v in rc if ft.child_off[v] != ft.child_off[v + 1])
+    def kids_of(v):
+        return list(ft.child_idx[ft.child_off[v]:ft.child_off[v + 1]])
+
+    def is_leaf(v):
+        return ft.child_off[v] == ft.child_off[v + 1]
+    n_edges_in_tables = 0
     for v in cherry_node.values():
-        kids = ft.child_idx[ft.child_off[v]:ft.child_off[v + 1]]
-        assert len(kids) == 2 and all(ft.child_off[x] == ft.child_off[x + 1] for x in kids) and v not in rc
+        kids = kids_of(v)
+        assert len(kids) == 2 and v not in rc
+        if all(is_leaf(x) for x in kids):
+            n_edges_in_tables += 3                                           # cherry: two tip edges + its own
+        else:                                                                # pitchfork: a cherry and a tip
+            inner = [x for x in kids if not is_leaf(x)]
+            assert len(inner) == 1 and all(is_leaf(y) for y in kids_of(inner[0])) and len(kids_of(inner[0])) == 2
+            n_edges_in_tables += 5
+    # every non-root edge is either in the matrix stream or inside a clade table
+    assert len(slot_node) + n_edges_in_tables == ft.n_nodes - 1 - sum(1 for v in rc if ft.child_off[v] != ft.child_off[v + 1])
+    row_off, acc_rows = {}, 0
+    for cid in sorted(cherry_node):
+        v = cherry_node[cid]
+        row_off[v] = acc_rows
+        acc_rows += 441 if all(is_leaf(x) for x in kids_of(v)) else 9261
     m = p.model
     K = len(p.rates)
     lnl, joint = [], []
@@ -45,17 +62,22 @@ def run_schedule(p, cols, rescale_every=8, cherry_tables=True):
                     return np.ones(20) if s >= 20 else np.eye(20)[s]
                 P = P_of(v)
                 return P.sum(axis=1) if s >= 20 else P[:, s]
-            def cherry(cid, row_a, row_b):
-                # what K1b tabulates: the cherry's own partial carried up its parent edge
-                v = cherry_node[cid]
-                a, b = ft.child_idx[ft.child_off[v]:ft.child_off[v + 1]]
-                return P_of(v) @ (tip(a, row_a) * tip(b, row_b))
+            def clade(v, rows):
+                # what K1b tabulates: the clade's own partial carried up its parent edge; `rows` = its tips' alignment
+                # rows in table-index order (cherry tips in child order, then the pitchfork's third tip)
+                kids = kids_of(v)
+                if all(is_leaf(x) for x in kids):
+                    a, b = kids
+                    return P_of(v) @ (tip(a, rows[0]) * tip(b, rows[1]))
+                inner = [x for x in kids if not is_leaf(x)][0]
+                t = [x for x in kids if is_leaf(x)][0]
+                return P_of(v) @ (clade(inner, rows[:2]) * tip(t, rows[2]))
             A, stack, cnt, slot, maxsp = None, [], 0, 0, 0
             parts = {}
             seen_cherries = 0
-            for w, r0, r1, r2, rb, rb2, _, _ in steps:
+            for w, r0, r1, r2, rb, rb2, rc1, rc2, ro1, ro2, _, _ in steps:
                 mv, n_pre, post = w & 3, (w >> 2) & 3, (w >> 5) & 1
-                ps, ps2, cid = (w >> 10) & 3, (w >> 12) & 3, (int(w) & 0xffffffff) >> 14
+                ps, ps2, tri1, tri2 = (w >> 10) & 3, (w >> 12) & 3, (w >> 14) & 1, (w >> 15) & 1
                 assert ps <= n_pre + post and (ps2 == 0 or ps < ps2 <= n_pre + post)
                 rows = [r0, r1, r2]
                 mv_node = None
@@ -66,9 +88,14 @@ def run_schedule(p, cols, rescale_every=8, cherry_tables=True):
                 def gather():
                     nonlocal slot, li, seen_cherries
                     li += 1
-                    if ps == li or ps2 == li:                              # the second one uses the next table
+                    if ps == li or ps2 == li:
+                        second = ps2 == li
+                        v = cherry_node[seen_cherries]                         # tables are numbered in order of use
                         seen_cherries += 1
-                        return cherry(cid + (ps2 == li), rows[li - 1], rb2 if ps2 == li else rb)
+                        assert (ro2 if second else ro1) == row_off[v]
+                        is_tri = not all(is_leaf(x) for x in kids_of(v))
+                        assert is_tri == bool(tri2 if second else tri1)
+                        return clade(v, [rows[li - 1], rb2 if second else rb, rc2 if second else rc1])
                     v = slot_node[slot]; slot += 1
                     return tip(v, rows[li - 1])
                 for i in range(n_pre):
@@ -118,8 +145,9 @@ def test_schedule_on_example(example_problem):
     # with cherry tables every collapsed cherry's contraction is gone, the results are the same
     got_l, got_j, steps_c, depth_c = run_schedule(p, cols)
     assert rel_err(got_l, lnl[cols]) < 1e-12 and rel_err(got_j, joint[cols]) < 1e-9
-    n_cherry = int(np.count_nonzero((steps_c[:, 0] >> 10) & 3) + np.count_nonzero((steps_c[:, 0] >> 12) & 3))
-    assert n_cherry >= 4 and int(np.count_nonzero(steps_c[:, 0] & 3)) == 15 - n_cherry and depth_c <= depth
+    w_ = steps_c[:, 0]
+    n_saved = int(sum(np.count_nonzero((w_ >> sh) & 3) for sh in (10, 12)) + np.count_nonzero(w_ & (1 << 14)) + np.count_nonzero(w_ & (1 << 15)))
+    assert n_saved >= 4 and int(np.count_nonzero(w_ & 3)) == 15 - n_saved and depth_c <= depth
 
 
 def test_schedule_shapes():
@@ -171,8 +199,10 @@ def test_schedule_synthetic(kind, n, depth_max):
     assert len(steps) <= n_mv + 4 + (0 if kind != "balanced" else n // 2)      # nearly every step carries an MMA burst
     got_l, got_j, steps_c, depth_c = run_schedule(p, range(3))
     assert rel_err(got_l, lnl) < 1e-12 and rel_err(got_j, joint) < 1e-9 and depth_c <= depth
-    n_cherry = int(np.count_nonzero((steps_c[:, 0] >> 10) & 3) + np.count_nonzero((steps_c[:, 0] >> 12) & 3))
-    n_mv_c = int(np.count_nonzero(steps_c[:, 0] & 3))
-    assert n_mv_c == n_mv - n_cherry
-    assert n_cherry >= {"balanced": n // 2 - 2, "yule": n // 4, "caterpillar": 1}[kind]
+    w_ = steps_c[:, 0]
+    # contractions saved: one per cherry table, two per pitchfork table
+    n_saved = int(sum(np.count_nonzero((w_ >> sh) & 3) for sh in (10, 12)) + np.count_nonzero(w_ & (1 << 14)) + np.count_nonzero(w_ & (1 << 15)))
+    n_mv_c = int(np.count_nonzero(w_ & 3))
+    assert n_mv_c == n_mv - n_saved
+    assert n_saved >= {"balanced": n // 2 - 2, "yule": n // 4, "caterpillar": 1}[kind]
     print(kind, "steps", len(steps), "->", len(steps_c), "contractions", n_mv, "->", n_mv_c)
