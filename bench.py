@@ -325,7 +325,7 @@ def run_b200(a):
     traffic = None
     try:
         if (a.taxa, a.columns, a.ncat, a.model) == (1000, 1_000_000, 4, "wag"):
-            prof_json = json.load(open(os.path.join(ROOT, "profiles", "r01_prune_kernel_realloc_ncu_full_1Mcols.json")))
+            prof_json = json.load(open(os.path.join(ROOT, "profiles", "r01_prune_kernel_clade_tables_ncu_full_1Mcols.json")))
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
             traffic = sum(float(prof_json[k]["value"]) * scale[prof_json[k]["unit"]]
                           for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
@@ -338,9 +338,10 @@ def run_b200(a):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / peak_tflops, "traffic": traffic,
                          "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of prune_kernel from "
-                                         "profiles/r01_prune_kernel_realloc_ncu_full_1Mcols.json; the kernel's own HBM need is "
-                                         "K*N bytes of states in + K*328 bytes of root partials out per column = 5.3 GB per launch "
-                                         "(0.5 % of the HBM roof: the path is FP64-tensor-bound, not HBM-bound)",
+                                         "profiles/r01_prune_kernel_clade_tables_ncu_full_1Mcols.json; the kernel's own HBM need is "
+                                         "K*N bytes of states in + K*328 bytes of root partials out per column = 5.3 GB per launch, plus "
+                                         "the rows of the clade tables that miss L2 (0.8 GB measured; L2 hit rate 92 %) "
+                                         "(0.9 % of the HBM roof: the path is FP64-tensor-bound, not HBM-bound)",
                          "kernel": "prune_kernel (FP64 DMMA m8n8k4)", "kernel_ms": k2_ms,
                          "kernel_share_of_step": prof["ms_prune"] / ms if world == 1 else None,
                          "flops_per_column": flops_per_col,
