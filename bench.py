@@ -167,7 +167,7 @@ def run_reference(a):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -376,14 +376,31 @@ def run_b200(a):
                       "C port with -O2, so it flatters the JVM",
             "variants": res}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints to fd 1 during the run
+    (NCCL's version banner, for one) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     a = parse_args()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)                          # C-level and Python-level stdout of this process now land on stderr
     if a.impl == "reference":
         return run_reference(a)
     return run_b200(a)
