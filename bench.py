@@ -354,7 +354,7 @@ def run_b200(a):
                          "peak_source": "live DMMA probe (sr_measure_fp64_peak) on this GPU; MEASURED_PEAKS.json has no FP64 entry; "
                                         "nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s"},
             "e2e": e2e, "e2e_compact": e2e_compact, "numa_node": numa_node, "gpu_launches": launches,
-            "kernel_ms": {"pbuild": prof["ms_pbuild"] / max(1, prof["n_pbuild"]), "prune": k2_ms,
+            "kernel_ms": {"pbuild_and_clade_tables_per_step": prof["ms_pbuild"] / max(1, a.steps), "prune": k2_ms,
                           "root": prof["ms_root"] / max(1, prof["n_root"])},
             "clocks": clocks, "total_lnl": total_lnl,
             "schedule": {"steps": info["n_steps"], "stack_depth": info["stack_depth"]}}

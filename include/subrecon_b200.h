@@ -55,7 +55,7 @@ typedef struct {
 /* Per-kernel device timings accumulated since the last sr_profile_reset (CUDA events on the
  * launching stream). ms_* are sums over launches. */
 typedef struct {
-    double  ms_pbuild;  int64_t n_pbuild;       /* K1: transition-matrix builder      */
+    double  ms_pbuild;  int64_t n_pbuild;       /* K1 + K1b: matrix and clade-table builders (launches of both) */
     double  ms_prune;   int64_t n_prune;        /* K2: post-order pruning (dominant)  */
     double  ms_root;    int64_t n_root;         /* K3: root-branch joint / marginal   */
     int64_t columns_pruned;                     /* columns processed by K2 launches   */

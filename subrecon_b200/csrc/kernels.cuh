@@ -187,13 +187,14 @@ struct CherryParams {
     int64_t rate_stride;       // doubles per rate class
 };
 
-// Dynamic shared memory (pitchforks only): U[441][20], the absorbed cherry's vector per state pair.
+// Dynamic shared memory (pitchforks only): U[441][20], the absorbed cherry's vector per state pair. grid (n, K, slices).
 __global__ void __launch_bounds__(256) cherry_kernel(CherryParams p) {
     __shared__ double iexp[NS * NS];
     __shared__ double Pm[5][NS * NS];
     __shared__ double Tt[3][21 * NS];                  // Tt[m][s][k] = P_m[k][s] for tips a, b, t; s = 20: row sum of P_m
     extern __shared__ __align__(16) double U[];
     const int cid = blockIdx.x, kr = blockIdx.y, tid = threadIdx.x;
+    const int slice = blockIdx.z, stride = 256 * gridDim.z;     // the table's rows are split over gridDim.z CTAs
     const int kind = p.kind[cid];
     const double rate = p.rates[kr];
     for (int m = 0; m < (kind == 3 ? 5 : 3); ++m) {
@@ -227,21 +228,35 @@ __global__ void __launch_bounds__(256) cherry_kernel(CherryParams p) {
     }
     __syncthreads();
     double* out = p.ctab + (size_t)kr * p.rate_stride + (size_t)p.rowoff[cid] * CHERRY_ROW_DOUBLES;
-    if (kind == 2) {
-        for (int e = tid; e < CHERRY_ROWS * CHERRY_ROW_DOUBLES; e += 256) {
-            const int row = e / CHERRY_ROW_DOUBLES, col = e % CHERRY_ROW_DOUBLES, grp = col / 6, r = col % 6;
-            double v = 0.0;
-            if (r < 5) {
-                const int i = grp * 5 + r, sa = row / 21, sb = row % 21;
-                const double* ta = Tt[0] + sa * NS;
-                const double* tb = Tt[1] + sb * NS;
-                const double* pv = Pm[2] + i * NS;
+    // One thread per table row: the row's operand w[k] (tip product, or cherry vector x third tip) is formed once and kept
+    // in registers; the top node's matrix is then read with warp-uniform (broadcast) addresses. Same operation order as
+    // the reference for every entry: sum over k ascending of P[i][k] * w[k], separate multiply and add.
+    auto emit_row = [&](int row, const double (&w)[NS]) {
+        double* o = out + (size_t)row * CHERRY_ROW_DOUBLES;
+#pragma unroll 1
+        for (int grp = 0; grp < 4; ++grp) {
+            double v[6];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                const double* pv = Pm[2] + (grp * 5 + r) * NS;
                 double s = 0.0;
 #pragma unroll
-                for (int k = 0; k < NS; ++k) s = __dadd_rn(s, __dmul_rn(pv[k], __dmul_rn(ta[k], tb[k])));
-                v = s;
+                for (int k = 0; k < NS; ++k) s = __dadd_rn(s, __dmul_rn(pv[k], w[k]));
+                v[r] = s;
             }
-            out[e] = v;
+            v[5] = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; r += 2) *reinterpret_cast<double2*>(o + grp * 6 + r) = make_double2(v[r], v[r + 1]);
+        }
+    };
+    if (kind == 2) {
+        for (int row = tid + slice * 256; row < CHERRY_ROWS; row += stride) {
+            const double* ta = Tt[0] + (row / 21) * NS;
+            const double* tb = Tt[1] + (row % 21) * NS;
+            double w[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) w[k] = __dmul_rn(ta[k], tb[k]);
+            emit_row(row, w);
         }
         return;
     }
@@ -258,20 +273,13 @@ __global__ void __launch_bounds__(256) cherry_kernel(CherryParams p) {
     }
     __syncthreads();
     // ... then the top node: (cherry vector x third tip) carried up the node's own edge (matrix 2)
-    for (int e = tid; e < PITCHFORK_ROWS * CHERRY_ROW_DOUBLES; e += 256) {
-        const int row = e / CHERRY_ROW_DOUBLES, col = e % CHERRY_ROW_DOUBLES, grp = col / 6, r = col % 6;
-        double v = 0.0;
-        if (r < 5) {
-            const int i = grp * 5 + r, sab = row / 21, st = row % 21;
-            const double* u = U + sab * NS;
-            const double* tt = Tt[2] + st * NS;
-            const double* pv = Pm[2] + i * NS;
-            double s = 0.0;
+    for (int row = tid + slice * 256; row < PITCHFORK_ROWS; row += stride) {
+        const double* u = U + (row / 21) * NS;
+        const double* tt = Tt[2] + (row % 21) * NS;
+        double w[NS];
 #pragma unroll
-            for (int k = 0; k < NS; ++k) s = __dadd_rn(s, __dmul_rn(pv[k], __dmul_rn(u[k], tt[k])));
-            v = s;
-        }
-        out[e] = v;
+        for (int k = 0; k < NS; ++k) w[k] = __dmul_rn(u[k], tt[k]);
+        emit_row(row, w);
     }
 }
 

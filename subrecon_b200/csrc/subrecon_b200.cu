@@ -477,7 +477,9 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
         cp.rate_stride = stride;
         const int usm = CHERRY_ROWS * NS * (int)sizeof(double);              // the pitchforks' scratch (70.6 KB)
         CUDA_TRY(c, cudaFuncSetAttribute(cherry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, usm));
-        cherry_kernel<<<dim3(n_cherry, c->K), 256, usm, s>>>(cp);
+        prof_begin(c, s, 0, 0);
+        cherry_kernel<<<dim3(n_cherry, c->K, 8), 256, usm, s>>>(cp);
+        prof_end(c, s);
         CUDA_TRY(c, cudaGetLastError());
         CUDA_TRY(c, cudaStreamSynchronize(s));       // the staging arrays are host memory owned by the context; keep it simple
     }
