@@ -396,6 +396,48 @@ def test_polytomy_missing_data_custom_rates(ctx):
     assert abs(r["lnl"][2]) < 1e-9                                       # all-missing column: likelihood 1
 
 
+CLADE_SHAPES = [
+    "(((a:0.1,b:0.2):0.1,c:0.3):0.2,((d:0.1,(e:0.2,f:0.1):0.3):0.1,g:0.2):0.1);",                    # pitchforks, tip first / last
+    "((((a:0.1,b:0.2):0.1,c:0.3):0.2,((d:0.1,e:0.2):0.3,f:0.1):0.1):0.05,((g:0.2,h:0.1):0.2,(i:0.3,j:0.1):0.1):0.3);",  # sibling pitchforks, sibling cherries
+    "((a:0.1,b:0.2):0.1,((c:0.3,d:0.1):0.2,e:0.4):0.3);",                                             # cherry / pitchfork AS root children: kept
+    "(((((a:0.1,b:0.1):0.1,c:0.1):0.1,d:0.1):0.1,e:0.2):0.1,((f:0.1,g:0.3):0.2,((h:0.1,i:0.1):0.2,(j:0.2,(k:0.1,l:0.3):0.1):0.1):0.2):0.1);",
+    "((a:0.2,b:0.01,(g:0.1,h:0.2):0.0,(i:0.1,(j:0.2,k:0.3):0.1):0.2):0.1,((c:0.3,d:0.05):0.1,(e:0.6,f:0.1):0.02,m:0.3):0.02);",   # below polytomies
+]
+
+
+@pytest.mark.parametrize("newick", CLADE_SHAPES)
+def test_clade_table_shapes(ctx, newick):
+    """Every way a cherry or pitchfork table can enter a step (before / after the contraction, two per step, next to real
+    tips, under polytomies, not at the root), with missing data, against the oracle; and against the table-free path."""
+    tree = treeio.parse_newick(newick)
+    flat = treeio.flatten_tree(tree)
+    n_tips = len(tree.leaves())
+    rng = np.random.default_rng(len(newick))
+    states = rng.integers(0, 22, size=(n_tips, 700)).astype(np.uint8)
+    states[states >= 20] = 255
+    model = oracle.OracleModel("Dayhoff")
+    rates = oracle.gamma_rates(3, 0.8)
+    lnl, joint = oracle.run(flat, states, model, rates)
+    _, node_slot, _ = native.schedule_dump(flat)
+    ctx.set_option("tile_m", 2)
+    ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
+    ctx.set_rates(rates)
+    ctx.set_tree(flat)
+    ctx.set_alignment(states)
+    r = ctx.run()
+    assert lnl_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
+    if "AS root" not in newick and newick != CLADE_SHAPES[2]:
+        assert np.count_nonzero(node_slot <= -2) >= 2
+    try:
+        ctx.set_option("cherry_tables", 0)
+        r0 = ctx.run()
+    finally:
+        ctx.set_option("cherry_tables", 1)
+    assert lnl_err(r0["lnl"], lnl) < TOL and rel_err(r["joint"], r0["joint"]) < 1e-10
+    st = ctx.run_streamed(states)
+    assert np.array_equal(st["lnl"], r["lnl"]) and np.array_equal(st["joint"], r["joint"])
+
+
 def test_leaf_as_root_child(ctx):
     """K=1 works in the reference (length-1 shortcut, utils/Utils.java:56-58); K>1 makes the reference throw for
     that column — the native path returns the well-defined limit instead (documented)."""
