@@ -60,3 +60,14 @@ def lnl_err(got, want):
     """|delta| / max(1, |lnL|): a log-likelihood near 0 (all-missing column) has no meaningful relative error."""
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     return float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want)))) if got.size else 0.0
+
+
+def random_newick(rng, n_tips):
+    """Random rooted topology (binary root, occasional polytomies below it, some zero-length branches) for fuzz tests."""
+    nodes = [f"t{i}:{rng.uniform(0.01, 0.5):.3f}" for i in range(n_tips)]
+    while len(nodes) > 2:
+        k = 2 if (rng.random() < 0.85 or len(nodes) < 5) else 3
+        idx = set(int(i) for i in rng.choice(len(nodes), size=k, replace=False))
+        sub = "(" + ",".join(nodes[i] for i in sorted(idx)) + f"):{rng.uniform(0.0, 0.4):.3f}"
+        nodes = [x for i, x in enumerate(nodes) if i not in idx] + [sub]
+    return "(" + ",".join(nodes) + ");"

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import lnl_err, load_example, rel_err, synthetic
+from helpers import lnl_err, load_example, random_newick, rel_err, synthetic
 from oracle import oracle
 from subrecon_b200 import native, recon, treeio
 
@@ -436,6 +436,31 @@ def test_clade_table_shapes(ctx, newick):
     assert lnl_err(r0["lnl"], lnl) < TOL and rel_err(r["joint"], r0["joint"]) < 1e-10
     st = ctx.run_streamed(states)
     assert np.array_equal(st["lnl"], r["lnl"]) and np.array_equal(st["joint"], r["joint"])
+
+
+def test_random_trees_fuzz(ctx):
+    """Random topologies (polytomies, zero branches), rate-class counts, models and missing data through the ABI."""
+    rng = np.random.default_rng(77)
+    for it in range(16):
+        n = int(rng.integers(4, 60))
+        tree = treeio.parse_newick(random_newick(rng, n))
+        flat = treeio.flatten_tree(tree)
+        rc = flat.child_idx[flat.child_off[flat.root]:flat.child_off[flat.root + 1]]
+        leaf_root = any(flat.child_off[v] == flat.child_off[v + 1] for v in rc)
+        K = 1 if leaf_root else int(rng.integers(1, 6))
+        states = rng.integers(0, 22, size=(n, 257 + 13 * it)).astype(np.uint8)
+        states[states >= 20] = 255
+        model = oracle.OracleModel(["WAG", "JTT", "Dayhoff", "BLOSUM62"][it % 4])
+        rates = oracle.gamma_rates(K, 0.6) if K > 1 else np.array([1.0])
+        lnl, joint = oracle.run(flat, states, model, rates)
+        ctx.set_option("tile_m", 2 if it % 5 else 4)
+        ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
+        ctx.set_rates(rates)
+        ctx.set_tree(flat)
+        ctx.set_alignment(states)
+        r = ctx.run()
+        assert lnl_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL, (it, tree.to_newick())
+    ctx.set_option("tile_m", 2)
 
 
 def test_leaf_as_root_child(ctx):

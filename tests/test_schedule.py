@@ -3,7 +3,7 @@ small numpy stack machine with the oracle's matrices and must reproduce the orac
 import numpy as np
 import pytest
 
-from helpers import load_example, rel_err, synthetic
+from helpers import load_example, random_newick, rel_err, synthetic
 from oracle import oracle
 from subrecon_b200 import native, synth, treeio
 
@@ -206,3 +206,27 @@ def test_schedule_synthetic(kind, n, depth_max):
     assert n_mv_c == n_mv - n_saved
     assert n_saved >= {"balanced": n // 2 - 2, "yule": n // 4, "caterpillar": 1}[kind]
     print(kind, "steps", len(steps), "->", len(steps_c), "contractions", n_mv, "->", n_mv_c)
+
+
+def test_schedule_fuzz():
+    """Random topologies (polytomies, tips as root children, zero branches), rate-class counts and rescale periods: the
+    collapsed (clade tables) and the plain schedule both reproduce the oracle on the CPU stack machine."""
+    class P:
+        pass
+    rng = np.random.default_rng(20261020)
+    for it in range(30):
+        n = int(rng.integers(3, 36))
+        tree = treeio.parse_newick(random_newick(rng, n))
+        p = P()
+        p.flat = treeio.flatten_tree(tree)
+        rc = p.flat.child_idx[p.flat.child_off[p.flat.root]:p.flat.child_off[p.flat.root + 1]]
+        leaf_root = any(p.flat.child_off[v] == p.flat.child_off[v + 1] for v in rc)
+        K = 1 if leaf_root else int(rng.integers(1, 4))           # the reference only handles a tip below the root for K = 1
+        p.states = rng.integers(0, 22, size=(n, 3)).astype(np.uint8)
+        p.states[p.states >= 20] = 255
+        p.model = oracle.OracleModel(["WAG", "JTT", "Dayhoff", "BLOSUM62"][it % 4])
+        p.rates = oracle.gamma_rates(K, 0.7) if K > 1 else np.array([1.0])
+        lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
+        for ct in (True, False):
+            got_l, got_j, _, _ = run_schedule(p, range(3), rescale_every=int(rng.integers(1, 9)), cherry_tables=ct)
+            assert np.max(np.abs(got_l - lnl) / np.maximum(1.0, np.abs(lnl))) < 1e-11 and rel_err(got_j, joint) < 1e-9
