@@ -191,6 +191,39 @@ def test_cfg4_deep_caterpillar_rescaling(ctx):
     ctx.set_option("rescale_every", 8)
 
 
+@pytest.mark.parametrize("shape", ["caterpillar", "balanced"])
+def test_adversarial_underflow(ctx, shape):
+    """The fastest a partial can shrink: every branch at the 1e-9 clamp, neighbouring tips always in conflicting states,
+    and those states carry floor-level frequencies — each merge costs ~20 orders of magnitude. The power-of-two rescale
+    every `rescale_every` edges must keep every partial inside FP64 (DESIGN.md, K2 'Rescaling': with the default of 8 there
+    is head-room; 12 still passes this case, 16 does not)."""
+    from subrecon_b200 import synth
+    n = 96
+    tree = (synth.caterpillar_tree if shape == "caterpillar" else synth.balanced_tree)(n, seed=1)
+    for v in range(len(tree.blen)):
+        tree.blen[v] = 0.0                                               # -> clamped to 1e-9 times the rate
+    flat = treeio.flatten_tree(tree)
+    freqs = np.full(20, 1.0)
+    freqs[[3, 7, 11]] = 1e-12                                            # PAL's clean-up lifts these to its floor
+    model = oracle.OracleModel("WAG", frequencies=freqs / freqs.sum())
+    rates = oracle.gamma_rates(2, 0.5)
+    rng = np.random.default_rng(5)
+    states = np.empty((n, 300), dtype=np.uint8)
+    rare = np.array([3, 7, 11], dtype=np.uint8)
+    for col in range(300):
+        states[:, col] = rare[(np.arange(n) + rng.integers(0, 3)) % 3] if col % 2 else rare[rng.integers(0, 3, size=n)]
+    lnl, joint = oracle.run(flat, states, model, rates)
+    assert lnl.min() < -1500 and np.isfinite(lnl).all()
+    ctx.set_option("tile_m", 2)
+    ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
+    ctx.set_rates(rates)
+    ctx.set_tree(flat)
+    ctx.set_alignment(states)
+    r = ctx.run()
+    assert np.isfinite(r["lnl"]).all() and np.isfinite(r["joint"]).all()
+    assert lnl_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
+
+
 def test_cfg4_full_size_properties(ctx):
     """BASELINE config #4 at full size (5,000-taxon caterpillar x 200k sites, K=8): 1,024 simulated columns repeated;
     every copy bit-identical, the first block equal to the oracle, posteriors sum to 1."""
