@@ -111,17 +111,18 @@ int sr_run_streamed(sr_ctx *ctx, int32_t n_taxa, int64_t n_sites, const uint8_t 
 void *sr_host_alloc(size_t bytes);
 void sr_host_free(void *p);
 
-/* Tuning / introspection. Options: "tile_m" (MMA column tiles per warp: 2 or 4), "warps" (consumer warps per
- * CTA: 8, 11, 15, or 12 = experimental variant without a producer warp), "holes" (0..2 pauses inside a warp's MMA burst), "rotate" (0/1 burst hand-off between the warps of
- * an SM sub-partition), "compress_patterns" (0/1: compute each distinct column pattern of a batch once and copy the
- * result to its duplicates; off by default), "prefetch" (experimental), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage), "stream_taper" (0/1: short pipeline
- * chunks at both ends of a streamed run, on by default), "input_chars" (0/1: alignment bytes are residue letters, see
- * sr_set_alignment), "cherry_tables" (0/1, default 1: tabulate every cherry's contribution per state pair once per rate
- * class and gather it instead of contracting it per column) with "cherry_table_mb" (memory cap, default 4096) "cherry_pairs"
- * (0/1, default 1: a step may gather two such clades) and "cherry_pitchforks" (0/1, default 1: the same one level up, a
- * cherry plus a tip, 9261 state triples), "realloc" (0/1, experimental: producer warp on re-allocated registers, 12 x tile_m 2 or
- * 8 x tile_m 4 consumer warps), "profile"
- * (0/1: record per-kernel events), "rescale_every" (edges between power-of-two rescalings). */
+/* Tuning / introspection. Options: "tile_m" (MMA column tiles per warp: 2 or 4), "warps" (consumer warps per CTA: 12 =
+ * default, on re-allocated registers; 8, 11, 15 = tuning variants), "realloc" (0/1: producer warp on re-allocated
+ * registers (setmaxnreg), 12 x tile_m 2 or 8 x tile_m 4 consumer warps), "holes" (pauses inside a warp's MMA burst: 0, 1, 2
+ * or the digits of the k-steps to pause before), "rotate" (0/1 burst hand-off between the warps of an SM sub-partition),
+ * "compress_patterns" (0/1: compute each distinct column pattern of a batch once and copy the result to its
+ * duplicates; off by default), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage),
+ * "stream_taper" (0/1: short pipeline chunks at both ends of a streamed run, on by default), "input_chars" (0/1:
+ * alignment bytes are residue letters, see sr_set_alignment), "cherry_tables" (0/1, default 1: tabulate every cherry's
+ * contribution per state pair once per rate class and gather it instead of contracting it per column) with
+ * "cherry_table_mb" (memory cap, default 4096), "cherry_pairs" (0/1, default 1: a step may gather two such clades) and
+ * "cherry_pitchforks" (0/1, default 1: the same one level up, a cherry plus a tip, 9261 state triples), "profile"
+ * (0/1: record per-kernel events), "rescale_every" (edges between power-of-two rescalings, default 8). */
 int sr_set_option(sr_ctx *ctx, const char *name, int64_t value);
 int sr_get_profile(sr_ctx *ctx, sr_profile *out);     /* synchronises the context's streams */
 int sr_profile_reset(sr_ctx *ctx);

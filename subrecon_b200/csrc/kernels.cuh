@@ -461,12 +461,6 @@ __host__ __device__ constexpr int prune_bar_bytes(int nstage) { return ((2 * nst
 __device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-// INL: no dedicated producer warp. Ring position P is refilled by consumer warp (P mod W): once per iteration it probes
-// (non-blocking) the "empty" barrier of the stage its next position lives in and issues the TMA copies if every warp has
-// released it; it only blocks when it reaches a position it has not requested yet. All W_ warps of the CTA are consumers,
-// so each SM sub-partition gets the same number of MMA warps (with a producer warp, its sub-partition runs one consumer
-// short and its tensor pipe idles a third of the time).
-//
 // RA: register re-allocation (setmaxnreg). A sub-partition's register file holds three warps of 168 registers, so a
 // producer warp next to W_ = 11 consumers leaves its sub-partition one MMA warp short (tensor pipe ~53 % busy there
 // against ~79 % on the other three). With RA the CTA is launched as whole warpgroups and the last one (the producer plus
@@ -489,12 +483,12 @@ __host__ __device__ constexpr int next_hole(int mask, int s) {          // first
 __host__ __device__ constexpr int first_hole(int mask) { return next_hole(mask, 0); }
 __host__ __device__ constexpr int pairs_before(int kstep) { return kstep >= 5 ? 8 : (3 * kstep + 1) / 2; }   // 16-byte fragment pairs covering k-steps < kstep
 
-constexpr int prune_threads(int w, bool inl, bool ra) { return ra ? (w + 4) * 32 : (w + (inl ? 0 : 1)) * 32; }
+constexpr int prune_threads(int w, bool ra) { return ra ? (w + 4) * 32 : (w + 1) * 32; }
 
 // TWOPS: steps may carry two cherry gathers (schedules of trees with many pairs of sibling cherries).
-template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false, bool RA = false, bool TWOPS = false>
-__global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(PruneParams p) {
-    static_assert(!RA || (!INL && ((W_ == 12 && M == 2) || (W_ == 8 && M == 4))), "register re-allocation is laid out for 12 x M=2 or 8 x M=4 consumer warps");
+template <int M, int NSTAGE, int W_, int HOLES = 0, bool ROT = false, bool RA = false, bool TWOPS = false>
+__global__ void __launch_bounds__(prune_threads(W_, RA), 1) prune_kernel(PruneParams p) {
+    static_assert(!RA || ((W_ == 12 && M == 2) || (W_ == 8 && M == 4)), "register re-allocation is laid out for 12 x M=2 or 8 x M=4 consumer warps");
     using Cfg = PruneCfg<M, W_>;
     constexpr int W = Cfg::W;
     constexpr int S = Cfg::S;
@@ -561,7 +555,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
         }
         if (W_ == 12) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    } else if (!INL && warp == W) {
+    } else if (warp == W) {
         produce();
         return;
     }
@@ -578,37 +572,6 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
     const int bar_wait_id = sp4 * 4 + (rpos + n_rot - 1) % n_rot;         // armed by the previous warp in the rotation
     const int bar_pass_id = sp4 * 4 + rpos;
     bool first_burst = (rpos == 0);
-    // INL: this warp refills ring positions my_pos = warp, warp + W, warp + 2W, ... (cursor: work item / step / descriptor)
-    uint32_t my_pos = (uint32_t)warp;
-    int my_item = blockIdx.x, my_step = warp;
-    int4 my_d = make_int4(0, 0, 0, 0);
-    int my_off = 0;
-    int4 my_rowb = make_int4(0, 0, 0, 0);
-    auto my_normalise = [&]() {
-        while (my_item < n_items && my_step >= p.n_steps) { my_step -= p.n_steps; my_item += gridDim.x; }
-        if (my_item < n_items) { my_d = __ldg(p.steps + 3 * my_step); my_rowb = __ldg(p.steps + 3 * my_step + 1); my_off = __ldg(p.step_off + my_step); }
-    };
-    // try (or, if `block`, wait) to refill my next position; returns after at most one refill
-    auto my_refill = [&](bool block) {
-        if (my_item >= n_items) return;
-        // Only once this warp itself is past position my_pos - NSTAGE: then the stage's "empty" barrier is at most one
-        // phase behind and the parity test below is unambiguous (a single in-order producer gets this for free).
-        if (my_pos >= it + NSTAGE) return;
-        const int stg_ = my_pos % NSTAGE;
-        const uint32_t par_ = ((my_pos / NSTAGE) & 1) ^ 1;
-        bool ok = mbar_test_wait(&empty[stg_], par_);
-        if (!ok && block) { mbar_wait(&empty[stg_], par_); ok = true; }
-        if (!ok) return;
-        if (lane == 0) issue_step(my_pos, my_item, my_d, my_rowb, my_off, false);
-        __syncwarp();
-        my_pos += W;
-        my_step += W;
-        my_normalise();
-    };
-    if (INL) {
-        my_normalise();
-        if (warp < NSTAGE) my_refill(true);           // the first NSTAGE positions find their stages empty
-    }
     // release of the stage used by ring position `it` (all of this warp's reads of it are complete)
     auto release_stage = [&](int stage) {
         if (lane == 0) mbar_arrive(&empty[stage]);
@@ -633,18 +596,6 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
         constexpr int FIRST = pairs_before(next_hole(HMASK, 0));           // fragment pairs fetched before the burst
         int s0[M], s1[M], s2[M];
         double Bf[16];
-        if (PREF) {
-            // prologue of the work item: the operands every later step gets from its predecessor's burst hole
-            const int stage0 = it % NSTAGE;
-            mbar_wait(&full[stage0], (it / NSTAGE) & 1);
-            const unsigned char* stg0 = stages + stage0 * STAGE_BYTES;
-            const unsigned char* stb0 = stg0 + st_lane_off;
-            const double2* frag0 = reinterpret_cast<const double2*>(stg0) + lane;
-#pragma unroll
-            for (int j = 0; j < M; ++j) { s0[j] = stb0[j * 8]; s1[j] = stb0[S + j * 8]; s2[j] = stb0[2 * S + j * 8]; }
-#pragma unroll
-            for (int i = 0; i < FIRST; ++i) { const double2 v = frag0[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
-        }
         for (int step = 0; step < p.n_steps; ++step, ++it) {
             const int stage = it % NSTAGE;
             const uint32_t ph = (it / NSTAGE) & 1;
@@ -653,34 +604,22 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
             const int2 ro = ro_next;
             if (has_next) { w_next = __ldg(&p.steps[3 * (step + 1)].x); ro_next = __ldg(reinterpret_cast<const int2*>(p.steps + 3 * (step + 1) + 2)); }
             SR_TL(0);                                   // step begins
-            if (INL) my_refill(/*block=*/my_pos <= it);
             const int mv = w & ST_MV_MASK, n_pre = (w >> ST_NPRE_SHIFT) & 3;
             const unsigned char* stg = stages + stage * STAGE_BYTES;
             const double2* frag = reinterpret_cast<const double2*>(stg) + lane;
             const double* tab = reinterpret_cast<const double*>(stg + (mv ? FRAG_BYTES : 0)) + q * 5;
             const unsigned char* stb = stg + st_lane_off;
-            // PREF: this step's stage was already waited for (by the predecessor or the prologue); make sure the NEXT
-            // one has landed before the burst, because its first operands are fetched inside the burst
-            const uint32_t itn = it + 1;
-            const unsigned char* stgn = stages + (itn % NSTAGE) * STAGE_BYTES;
-            int sn0[M], sn1[M], sn2[M];
-            if (PREF) {
-                if (has_next && !next_ready) mbar_wait(&full[itn % NSTAGE], (itn / NSTAGE) & 1);
-            } else {
-                if (!next_ready) mbar_wait(&full[stage], ph);
-            }
+            if (!next_ready) mbar_wait(&full[stage], ph);
             next_ready = false;
             SR_TL(1);                                   // stage has landed
 
             // ---- all shared-memory reads of the step are issued up front
-            if (!PREF) {
 #pragma unroll
-                for (int j = 0; j < M; ++j) { s0[j] = stb[j * 8]; s1[j] = stb[S + j * 8]; s2[j] = stb[2 * S + j * 8]; }
-            }
+            for (int j = 0; j < M; ++j) { s0[j] = stb[j * 8]; s1[j] = stb[S + j * 8]; s2[j] = stb[2 * S + j * 8]; }
             // The burst is issued in HOLES+1 chunks; the fragments of chunk c+1 are loaded only after chunk c was issued,
             // so the warp pauses for one LDS latency inside its own burst. Sibling warps' Hadamard DMULs (same FP64 pipe)
             // slip into those holes instead of starving until the whole burst is over (which bunches the warps).
-            if (mv && !PREF) {
+            if (mv) {
 #pragma unroll
                 for (int i = 0; i < FIRST; ++i) { const double2 v = frag[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
             }
@@ -825,15 +764,6 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
                         const int lo = pairs_before(s), hi = pairs_before(next_hole(HMASK, s));
 #pragma unroll
                         for (int i = lo; i < hi; ++i) { const double2 v = frag[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
-                        if (PREF && s == first_hole(HMASK) && has_next) {
-                            // fragments 0..5 are dead (k-steps 0,1 issued): refill them, and the tip state codes, for step+1
-                            const double2* fragn = reinterpret_cast<const double2*>(stgn) + lane;
-                            const unsigned char* stbn = stgn + st_lane_off;
-#pragma unroll
-                            for (int i = 0; i < FIRST; ++i) { const double2 v = fragn[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
-#pragma unroll
-                            for (int j = 0; j < M; ++j) { sn0[j] = stbn[j * 8]; sn1[j] = stbn[S + j * 8]; sn2[j] = stbn[2 * S + j * 8]; }
-                        }
                     }
 #pragma unroll
                     for (int j = 0; j < M; ++j)
@@ -859,7 +789,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
                     release_stage(stage);
                 }
                 {   // probe the next stage now: the ~60-cycle TRYWAIT latency hides behind this step's epilogue
-                    const uint32_t itp = it + (PREF ? 2 : 1);
+                    const uint32_t itp = it + 1;
                     next_ready = (p.debug & 2) ? false : mbar_test_wait(&full[itp % NSTAGE], (itp / NSTAGE) & 1);
                 }
                 if (LAZY) {
@@ -910,25 +840,7 @@ __global__ void __launch_bounds__(prune_threads(W_, INL, RA), 1) prune_kernel(Pr
                     stage_release(&empty[stage], lane);
                 }
             } else {
-                if (INL) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    release_stage(stage);
-                } else {
-                    stage_release(&empty[stage], lane);
-                }
-                if (PREF && has_next) {          // no burst to hide behind: fetch the next step's first operands here
-                    const double2* fragn = reinterpret_cast<const double2*>(stgn) + lane;
-                    const unsigned char* stbn = stgn + st_lane_off;
-#pragma unroll
-                    for (int i = 0; i < FIRST; ++i) { const double2 v = fragn[i * 32]; Bf[2 * i] = v.x; Bf[2 * i + 1] = v.y; }
-#pragma unroll
-                    for (int j = 0; j < M; ++j) { sn0[j] = stbn[j * 8]; sn1[j] = stbn[S + j * 8]; sn2[j] = stbn[2 * S + j * 8]; }
-                }
-            }
-            if (PREF && has_next) {
-#pragma unroll
-                for (int j = 0; j < M; ++j) { s0[j] = sn0[j]; s1[j] = sn1[j]; s2[j] = sn2[j]; }
+                stage_release(&empty[stage], lane);
             }
             SR_TL(6);                                   // epilogue products issued
             // rescale / push / store of the step's result, wherever it lives: in A, or (plain MV) still in the accumulators.

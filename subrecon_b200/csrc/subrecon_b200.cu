@@ -91,7 +91,6 @@ struct sr_ctx {
     int64_t cherry_table_mb = 4096;     // memory cap for those tables; clades beyond it are pruned the ordinary way
     bool input_chars = false;           // alignment bytes are residue letters, translated on the device
     int compress = 0;                   // reduce every batch to its distinct column patterns first
-    int prefetch = 0;                   // fetch the next step's first operands inside the current MMA burst
     int rotate = 1;                     // named-barrier burst rotation among the warps of an SM sub-partition
     int warps = 12;                     // consumer warps per CTA (tile_m == 2: 8, 11, 12 or 15)
     bool realloc = true;                // producer warp on re-allocated registers (setmaxnreg): 12 x tile_m 2 or 8 x tile_m 4 consumers
@@ -176,7 +175,7 @@ int build_schedule(sr_ctx* c) {
     std::vector<int32_t> cherry_of(n, -1);       // 2 / 3 = collapsed cherry / pitchfork (replaced by the table index below)
     c->cherry_node.clear(); c->cherry_kind.clear(); c->cherry_rowoff.clear(); c->cherry_blen.clear();
     c->ctab_rows = 0;
-    if (c->cherry_tables && !c->prefetch) {
+    if (c->cherry_tables) {
         const int64_t row_bytes = (int64_t)std::max(1, c->K) * CHERRY_ROW_DOUBLES * (int64_t)sizeof(double);
         int64_t rows_left = (c->cherry_table_mb << 20) / row_bytes;
         int n_tab = 0;
@@ -271,7 +270,7 @@ int build_schedule(sr_ctx* c) {
     }
     if (c->ctab_rows > INT32_MAX) return fail(c, SR_ERR_UNSUPPORTED, "clade tables too large for 32-bit row offsets; lower cherry_table_mb");
     // (two cherry gathers per step only for the default kernel layout: the tuning variants are single-gather builds)
-    const bool default_layout = c->tile_m == 2 && c->warps == 12 && c->realloc && !c->prefetch && c->holes == 2;
+    const bool default_layout = c->tile_m == 2 && c->warps == 12 && c->realloc && c->holes == 2;
     const int max_pseudo = (c->cherry_pairs && default_layout) ? 2 : 1;
     // ---- fuse into steps: [<=2 tip gathers] [one MV] [<=1 tip gather]; a push/store ends its step
     c->steps.clear(); c->step_off.clear();
@@ -487,7 +486,7 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     return SR_OK;
 }
 
-template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false, bool PREF = false, bool INL = false, bool RA = false, bool TWOPS = false>
+template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false, bool RA = false, bool TWOPS = false>
 int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     using Cfg = PruneCfg<M, W>;
     const int fixed = NSTAGE * Cfg::STAGE_BYTES + prune_bar_bytes(NSTAGE);
@@ -502,10 +501,10 @@ int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
     p.spill_levels = spill_levels;
     p.spill = c->d_spill.as<double>();
     const int smem = fixed + levels * Cfg::LEVEL_BYTES;
-    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT, PREF, INL, RA, TWOPS>;
+    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT, RA, TWOPS>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prof_begin(c, s, 1, cols);
-    kern<<<grid, prune_threads(W, INL, RA), smem, s>>>(p);
+    kern<<<grid, prune_threads(W, RA), smem, s>>>(p);
     prof_end(c, s);
     CUDA_TRY(c, cudaGetLastError());
     return SR_OK;
@@ -549,36 +548,34 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
 #endif
     // kernel variants: tile_m (column tiles per warp), consumer warps, holes in the MMA burst, burst rotation
     const int hl = c->holes, rot = c->rotate;
+    // template arguments: <tile_m, ring stages, consumer warps, holes, rotation, register re-allocation, two clade gathers>
     if (c->has_pairs) {
-        // schedules with two cherry gathers in a step run on the default layout's two-gather build (the tuning variants
-        // below are single-gather builds; "cherry_pairs" = 0 gives them a schedule they can run)
-        if (!(c->tile_m == 2 && c->warps == 12 && c->realloc && !c->prefetch && hl == 2))
-            return fail(c, SR_ERR_UNSUPPORTED, "internal: schedule with cherry pairs on a single-gather kernel variant");
-        rc = rot ? launch_prune<2, 4, 12, 2, true, false, false, true, true>(c, s, p, n)
-                 : launch_prune<2, 4, 12, 2, false, false, false, true, true>(c, s, p, n);
-    } else if (c->tile_m == 4 && c->realloc) rc = rot ? launch_prune<4, 4, 8, 2, true, false, false, true>(c, s, p, n) : launch_prune<4, 4, 8, 0, false, false, false, true>(c, s, p, n);
-    else if (c->tile_m == 4) rc = launch_prune<4, 4, 8>(c, s, p, n);
-    else if (c->warps == 12 && c->realloc && rot && hl == 0) rc = launch_prune<2, 4, 12, 0, true, false, false, true>(c, s, p, n);
-    else if (c->warps == 12 && c->realloc && rot && hl == 1) rc = launch_prune<2, 4, 12, 1, true, false, false, true>(c, s, p, n);
-    else if (c->warps == 12 && c->realloc && rot && hl == 13) rc = launch_prune<2, 4, 12, 13, true, false, false, true>(c, s, p, n);
-    else if (c->warps == 12 && c->realloc && rot && hl == 123) rc = launch_prune<2, 4, 12, 123, true, false, false, true>(c, s, p, n);
-    else if (c->warps == 12 && c->realloc && rot && hl == 234) rc = launch_prune<2, 4, 12, 234, true, false, false, true>(c, s, p, n);
-    else if (c->warps == 12 && c->realloc && rot && hl == 1234) rc = launch_prune<2, 4, 12, 1234, true, false, false, true>(c, s, p, n);
-    else if (c->warps == 12 && c->realloc) rc = rot ? launch_prune<2, 4, 12, 2, true, false, false, true>(c, s, p, n) : launch_prune<2, 4, 12, 2, false, false, false, true>(c, s, p, n);
-    else if (c->warps == 12) rc = rot ? launch_prune<2, 4, 12, 2, true, false, true>(c, s, p, n) : launch_prune<2, 4, 12, 2, false, false, true>(c, s, p, n);
-    else if (c->warps == 8) rc = rot ? launch_prune<2, 4, 8, 2, true>(c, s, p, n) : launch_prune<2, 4, 8, 0, false>(c, s, p, n);
-    else if (c->warps == 15) rc = rot ? launch_prune<2, 4, 15, 2, true>(c, s, p, n) : launch_prune<2, 4, 15, 0, false>(c, s, p, n);
-    else if (c->prefetch && rot) rc = launch_prune<2, 4, 11, 2, true, true>(c, s, p, n);
-    else if (c->prefetch) rc = launch_prune<2, 4, 11, 2, false, true>(c, s, p, n);
-    else if (rot && hl == 13) rc = launch_prune<2, 4, 11, 13, true>(c, s, p, n);
-    else if (rot && hl == 12) rc = launch_prune<2, 4, 11, 12, true>(c, s, p, n);
-    else if (rot && hl == 23) rc = launch_prune<2, 4, 11, 23, true>(c, s, p, n);
-    else if (rot && hl == 14) rc = launch_prune<2, 4, 11, 14, true>(c, s, p, n);
-    else if (rot && hl == 34) rc = launch_prune<2, 4, 11, 34, true>(c, s, p, n);
-    else if (rot) rc = (hl == 0) ? launch_prune<2, 4, 11, 0, true>(c, s, p, n)
-                     : (hl == 1) ? launch_prune<2, 4, 11, 1, true>(c, s, p, n) : launch_prune<2, 4, 11, 2, true>(c, s, p, n);
-    else rc = (hl == 0) ? launch_prune<2, 4, 11, 0, false>(c, s, p, n)
-            : (hl == 1) ? launch_prune<2, 4, 11, 1, false>(c, s, p, n) : launch_prune<2, 4, 11, 2, false>(c, s, p, n);
+        // schedules with two clade gathers in a step exist only for the default layout (build_schedule)
+        if (!(c->tile_m == 2 && c->warps == 12 && c->realloc && hl == 2))
+            return fail(c, SR_ERR_UNSUPPORTED, "internal: schedule with clade pairs on a single-gather kernel variant");
+        rc = rot ? launch_prune<2, 4, 12, 2, true, true, true>(c, s, p, n) : launch_prune<2, 4, 12, 2, false, true, true>(c, s, p, n);
+    } else if (c->tile_m == 4 && c->realloc) {
+        rc = rot ? launch_prune<4, 4, 8, 2, true, true>(c, s, p, n) : launch_prune<4, 4, 8, 0, false, true>(c, s, p, n);
+    } else if (c->tile_m == 4) {
+        rc = launch_prune<4, 4, 8>(c, s, p, n);
+    } else if (c->warps == 12) {                       // 12 consumers always run on re-allocated registers
+        if (!rot) rc = launch_prune<2, 4, 12, 2, false, true>(c, s, p, n);
+        else if (hl == 0) rc = launch_prune<2, 4, 12, 0, true, true>(c, s, p, n);
+        else if (hl == 1) rc = launch_prune<2, 4, 12, 1, true, true>(c, s, p, n);
+        else if (hl == 13) rc = launch_prune<2, 4, 12, 13, true, true>(c, s, p, n);
+        else if (hl == 1234) rc = launch_prune<2, 4, 12, 1234, true, true>(c, s, p, n);
+        else rc = launch_prune<2, 4, 12, 2, true, true>(c, s, p, n);
+    } else if (c->warps == 8) {
+        rc = rot ? launch_prune<2, 4, 8, 2, true>(c, s, p, n) : launch_prune<2, 4, 8, 0, false>(c, s, p, n);
+    } else if (c->warps == 15) {
+        rc = rot ? launch_prune<2, 4, 15, 2, true>(c, s, p, n) : launch_prune<2, 4, 15, 0, false>(c, s, p, n);
+    } else {                                           // 11 consumers + producer, 168 registers
+        if (!rot) rc = (hl == 0) ? launch_prune<2, 4, 11, 0, false>(c, s, p, n) : launch_prune<2, 4, 11, 2, false>(c, s, p, n);
+        else if (hl == 0) rc = launch_prune<2, 4, 11, 0, true>(c, s, p, n);
+        else if (hl == 1) rc = launch_prune<2, 4, 11, 1, true>(c, s, p, n);
+        else if (hl == 13) rc = launch_prune<2, 4, 11, 13, true>(c, s, p, n);
+        else rc = launch_prune<2, 4, 11, 2, true>(c, s, p, n);
+    }
     if (rc) return rc;
     RootParams r{};
     r.rootpart = p.rootpart;
@@ -1025,12 +1022,13 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
         if (value != 8 && value != 11 && value != 12 && value != 15) return fail(c, SR_ERR_ARG, "warps must be 8, 11, 12 or 15");
         if (c->tile_m == 4 && value != 8) return fail(c, SR_ERR_ARG, "tile_m 4 supports 8 warps only");
         c->warps = (int)value;
-        c->realloc = false;
+        c->realloc = (value == 12);                  // 12 consumers only exist on re-allocated registers
         c->sched_dirty = true;
     } else if (k == "realloc") {
         // dedicated producer warp living on re-allocated registers (setmaxnreg): 12 consumers x tile_m 2, or 8 x tile_m 4
         c->realloc = value != 0;
         if (c->realloc) c->warps = (c->tile_m == 4) ? 8 : 12;
+        else if (c->tile_m == 2 && c->warps == 12) c->warps = 11;
         c->sched_dirty = true;
     } else if (k == "chunk_cols") {
         if (value < 256) return fail(c, SR_ERR_ARG, "chunk_cols must be >= 256");
@@ -1057,9 +1055,6 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
         c->sched_dirty = true;
     } else if (k == "input_chars") {
         c->input_chars = value != 0;                  // applies to the next sr_set_alignment / sr_run_streamed
-    } else if (k == "prefetch") {
-        c->prefetch = value != 0;
-        c->sched_dirty = true;                       // (the prefetching variant does not take cherry gathers)
     } else if (k == "debug") {
         c->debug = (int)value;
     } else if (k == "rotate") {

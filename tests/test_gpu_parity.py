@@ -277,7 +277,7 @@ def test_cfg5_subset(ctx):
 @pytest.mark.parametrize("opts", [dict(tile_m=4), dict(tile_m=4, realloc=1), dict(tile_m=4, realloc=1, rotate=0), dict(warps=8), dict(warps=15),
                                   dict(warps=8, rotate=0), dict(holes=0), dict(holes=1), dict(holes=13), dict(holes=1234), dict(rotate=0),
                                   dict(warps=11), dict(warps=11, rotate=0), dict(warps=11, holes=0), dict(warps=11, holes=0, rotate=0),
-                                  dict(warps=11, prefetch=1), dict(warps=11, prefetch=1, rotate=0), dict(warps=12), dict(warps=12, rotate=0),
+                                  dict(warps=12), dict(warps=12, rotate=0),
                                   dict(cherry_tables=0), dict(cherry_tables=0, warps=11), dict(cherry_tables=0, tile_m=4), dict(cherry_table_mb=1), dict(cherry_table_mb=40), dict(cherry_pairs=0), dict(cherry_pitchforks=0), dict(cherry_pitchforks=0, cherry_pairs=0),
                                   dict(cherry_pairs=0, rotate=0)])
 def test_kernel_variants_agree(ctx, opts):
@@ -291,7 +291,7 @@ def test_kernel_variants_agree(ctx, opts):
         r = ctx.run()
         assert rel_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
     finally:
-        for k, v in dict(tile_m=2, holes=2, rotate=1, prefetch=0, cherry_tables=1, cherry_table_mb=4096, cherry_pairs=1, cherry_pitchforks=1).items():   # tile_m=2 restores the default warp layout
+        for k, v in dict(tile_m=2, holes=2, rotate=1, cherry_tables=1, cherry_table_mb=4096, cherry_pairs=1, cherry_pitchforks=1).items():   # tile_m=2 restores the default warp layout
             ctx.set_option(k, v)
 
 

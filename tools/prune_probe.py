@@ -17,7 +17,6 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--warps", type=int, default=0)
 ap.add_argument("--holes", type=int, default=-1)
 ap.add_argument("--rotate", type=int, default=-1)
-ap.add_argument("--prefetch", type=int, default=-1)
 ap.add_argument("--rescale", type=int, default=0)
 ap.add_argument("--debug", type=int, default=0)
 ap.add_argument("--taxa", type=int, default=1000)
@@ -43,8 +42,6 @@ if a.holes >= 0:
     ctx.set_option("holes", a.holes)
 if a.rescale:
     ctx.set_option("rescale_every", a.rescale)
-if a.prefetch >= 0:
-    ctx.set_option("prefetch", a.prefetch)
 if a.rotate >= 0:
     ctx.set_option("rotate", a.rotate)
 if a.warps == 13:
@@ -66,5 +63,5 @@ for _ in range(a.reps):
 p = ctx.profile(reset=True)
 ms = p["ms_prune"] / p["n_prune"]
 tf = info["flops_per_column_rate"] * len(rates) * a.cols / ms * 1e-9
-print(f"tree={a.tree} taxa={a.taxa} cols={a.cols} tile_m={a.tile_m} warps={a.warps} holes={a.holes} rotate={a.rotate} prefetch={a.prefetch} K={a.ncat} depth={info['stack_depth']} steps={info['n_steps']}: "
+print(f"tree={a.tree} taxa={a.taxa} cols={a.cols} tile_m={a.tile_m} warps={a.warps} holes={a.holes} rotate={a.rotate} K={a.ncat} depth={info['stack_depth']} steps={info['n_steps']}: "
       f"prune {ms:.3f} ms/launch  {a.cols / ms * 1e-3:.3f} Mcol/s  {tf:.2f} TFLOP/s  root {p['ms_root'] / p['n_root']:.3f} ms")
