@@ -182,7 +182,8 @@ def run_b200(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product arm has no CPU fallback")
     torch.cuda.set_device(local)
-    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
+    affinity0 = os.sched_getaffinity(0)
+    numa_node = bind_to_gpu_numa_node(local)          # page-locked buffers land on the GPU's NUMA node (first touch)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
@@ -361,6 +362,7 @@ def run_b200(a):
 
     # ---- cpu_baseline: the reference's CPU algorithm on this box's host cores (rank 0, N=1 only)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        os.sched_setaffinity(0, affinity0)               # the CPU baseline gets every host core back
         threads = os.cpu_count() or 1
         ctx.close()
         res = {}

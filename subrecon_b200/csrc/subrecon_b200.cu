@@ -104,13 +104,13 @@ struct sr_ctx {
     DevBuf d_model, d_rates, d_steps, d_stepoff, d_slotkind, d_slotoff, d_slotblen, d_pstream, d_proot, d_states, d_rootpart, d_rootexp, d_spill;
     DevBuf d_pat_keys[2], d_pat_idx[2], d_pat_h2, d_pat_head, d_pat_uid, d_pat_rep, d_pat_map, d_pat_tmp, d_pat_states, d_pat_lnl, d_pat_joint, d_pat_compact;
     int64_t last_unique = 0, last_total = 0;
-    DevBuf d_chunk_states[2], d_chunk_lnl[2], d_chunk_joint[2], d_chunk_compact[2], d_peak;
+    DevBuf d_chunk_states[3], d_chunk_lnl[3], d_chunk_joint[3], d_chunk_compact[3], d_peak;   // pipeline buffers (sr_run: 2, streamed: 3)
     int32_t aln_taxa = 0;
     int64_t aln_sites = 0, aln_pitch = 0;
 
     // pinned bounce buffers for pageable caller memory
-    void* h_bounce[2] = {nullptr, nullptr};
-    size_t h_bounce_cap[2] = {0, 0};
+    void* h_bounce[3] = {nullptr, nullptr, nullptr};
+    size_t h_bounce_cap[3] = {0, 0, 0};
 
     std::vector<EvPair> events;
     sr_profile prof{};
@@ -722,7 +722,7 @@ void sr_destroy(sr_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    for (int i = 0; i < 2; ++i) if (c->h_bounce[i]) cudaFreeHost(c->h_bounce[i]);
+    for (int i = 0; i < 3; ++i) if (c->h_bounce[i]) cudaFreeHost(c->h_bounce[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -891,7 +891,10 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
     CUDA_TRY(c, cudaSetDevice(c->device));
     rc = ensure_pstream(c, c->stream);
     if (rc) return rc;
-    // three-stage pipeline over column chunks: H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h), two buffers each
+    // three-stage pipeline over column chunks: H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h), NB buffers each. Three, not
+    // two: with two, the kernels of chunk i wait for the download of chunk i-2, and when chunk i-1 is a short one (the
+    // ramp at the end, the odd remainder) its kernels finish long before that download does — a whole chunk's D2H was exposed.
+    constexpr int NB = 3;
     // Pipeline chunk: about stream_chunk_cols columns, rounded to a whole number of persistent-kernel waves
     // (tiles x K work items must be a multiple of the SM count, or the last wave of every chunk runs part empty).
     int64_t chunk;
@@ -905,8 +908,8 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
         chunk = std::max<int64_t>(256, (chunk + 15) / 16 * 16);
     }
     const int64_t cpitch = (chunk + 255) / 256 * 256 + 256;
-    cudaEvent_t up_ev[2], done_ev[2], free_ev[2], sfree_ev[2];
-    for (int i = 0; i < 2; ++i) {
+    cudaEvent_t up_ev[NB], done_ev[NB], free_ev[NB], sfree_ev[NB];
+    for (int i = 0; i < NB; ++i) {
         CUDA_TRY(c, cudaEventCreateWithFlags(&up_ev[i], cudaEventDisableTiming));
         CUDA_TRY(c, cudaEventCreateWithFlags(&done_ev[i], cudaEventDisableTiming));
         CUDA_TRY(c, cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming));
@@ -915,29 +918,35 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
     const bool src_pinned = is_pinned(states);
     const bool pin_lnl = is_pinned(lnl), pin_joint = joint && is_pinned(joint), pin_compact = compact && is_pinned(compact);
     // Chunk sizes: full chunks in the middle, a ramp of short ones at both ends. The pipeline's exposed time is the
-    // upload of the first chunk plus the download of the last one (3200 B per column of joint output), so those two are
-    // made an eighth of a full chunk; each neighbour doubles, which keeps every copy hidden behind the kernels next to it.
+    // upload of the first chunk plus the download of the last one (3200 B per column of joint output).
     std::vector<int64_t> sizes;
     {
         const int64_t S = (int64_t)c->warps * c->tile_m * 8;
         int64_t g = c->n_sm, b = std::max(1, c->K);
         while (b) { const int64_t t = g % b; g = b; b = t; }
         const int64_t unit = (c->n_sm / g) * S;
-        int64_t ramp[3] = {0, 0, 0}, ramp_sum = 0;
-        if (c->stream_taper && chunk >= 8 * unit)
-            for (int i = 0; i < 3; ++i) { ramp[i] = std::max<int64_t>(unit, (chunk >> (3 - i)) / unit * unit); ramp_sum += ramp[i]; }
+        // head: 1/8, 1/4, 1/2 of a chunk (the first upload is what is exposed). tail: a geometric ramp with ratio 3/4 down to
+        // 1/8 — a download takes about two thirds of the time its chunk's kernels take, so each chunk's download is over
+        // before the next, 3/4 as long, has been computed, and only the last small one is exposed.
+        std::vector<int64_t> head, tail;
+        int64_t head_sum = 0, tail_sum = 0;
+        if (c->stream_taper && chunk >= 8 * unit) {
+            for (int i = 3; i >= 1; --i) { head.push_back(std::max<int64_t>(unit, (chunk >> i) / unit * unit)); head_sum += head.back(); }
+            for (int64_t t = chunk * 3 / 4; t >= chunk / 8; t = t * 3 / 4) { tail.push_back(std::max<int64_t>(unit, t / unit * unit)); tail_sum += tail.back(); }
+        }
         int64_t left = n;
-        if (ramp_sum && n >= 2 * ramp_sum + chunk) {
-            for (int i = 0; i < 3; ++i) { sizes.push_back(ramp[i]); left -= ramp[i]; }
-            while (left - ramp_sum >= chunk) { sizes.push_back(chunk); left -= chunk; }
-            if (left > ramp_sum) { sizes.push_back(left - ramp_sum); left = ramp_sum; }
-            for (int i = 2; i >= 0; --i) { sizes.push_back(ramp[i]); left -= ramp[i]; }
+        if (!head.empty() && n >= head_sum + tail_sum + chunk) {
+            for (int64_t h : head) { sizes.push_back(h); left -= h; }
+            const int64_t odd = (left - tail_sum) % chunk;                 // the remainder goes in front of the full chunks
+            if (odd > 0) { sizes.push_back(odd); left -= odd; }
+            while (left - tail_sum >= chunk) { sizes.push_back(chunk); left -= chunk; }
+            for (int64_t t : tail) { sizes.push_back(t); left -= t; }
         } else {
             while (left > 0) { const int64_t m = std::min(left, chunk); sizes.push_back(m); left -= m; }
         }
     }
     const int64_t mmax = std::min(n, chunk);
-    for (int b = 0; b < 2 && rc == SR_OK; ++b) {
+    for (int b = 0; b < NB && rc == SR_OK; ++b) {
         if (c->d_chunk_states[b].reserve((size_t)cpitch * n_taxa + 512) != cudaSuccess ||
             c->d_chunk_lnl[b].reserve(sizeof(double) * mmax) != cudaSuccess ||
             (joint && c->d_chunk_joint[b].reserve(sizeof(double) * 400 * mmax) != cudaSuccess) ||
@@ -945,13 +954,23 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
             cudaGetLastError();
             rc = fail(c, SR_ERR_OOM, "device OOM (pipeline chunk buffers)");
         }
-        if (sizes.size() < 2) break;
+        if ((int)sizes.size() <= b + 1) break;
     }
+#ifdef SR_TIMELINE
+    struct TlEv { cudaEvent_t h0, h1, k0, k1, d0, d1; int64_t m; };
+    std::vector<TlEv> tl(sizes.size());
+    for (auto& e : tl) { cudaEventCreate(&e.h0); cudaEventCreate(&e.h1); cudaEventCreate(&e.k0); cudaEventCreate(&e.k1); cudaEventCreate(&e.d0); cudaEventCreate(&e.d1); }
+#define SR_PIPE_EV(ev, st) cudaEventRecord(tl[ci].ev, st)
+    auto tl_set_m = [&](size_t i, int64_t mm) { tl[i].m = mm; };
+#else
+#define SR_PIPE_EV(ev, st) do { } while (0)
+    auto tl_set_m = [](size_t, int64_t) {};
+#endif
     int64_t done = 0;
     for (size_t ci = 0; ci < sizes.size() && rc == SR_OK; ++ci) {
-        const int b = (int)(ci & 1);
+        const int b = (int)(ci % NB);
         const int64_t m = sizes[ci];
-        if (ci >= 2) cudaStreamWaitEvent(c->s_h2d, sfree_ev[b], 0);     // kernels of chunk ci-2 have consumed states buffer b
+        if (ci >= NB) cudaStreamWaitEvent(c->s_h2d, sfree_ev[b], 0);    // kernels of chunk ci-NB have consumed states buffer b
         const uint8_t* src = states + site0 + done;
         int64_t src_pitch = pitch;
         if (!src_pinned) {
@@ -963,35 +982,53 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
                 if (c->h_bounce[b]) { cudaEventSynchronize(up_ev[b]); cudaFreeHost(c->h_bounce[b]); c->h_bounce[b] = nullptr; c->h_bounce_cap[b] = 0; }
                 if (cudaMallocHost(&c->h_bounce[b], need) != cudaSuccess) { cudaGetLastError(); rc = fail(c, SR_ERR_OOM, "cannot allocate the pinned staging buffer"); break; }
                 c->h_bounce_cap[b] = need;
-            } else if (ci >= 2) {
-                cudaEventSynchronize(up_ev[b]);                          // the DMA out of this bounce buffer (chunk ci-2) is done
+            } else if (ci >= NB) {
+                cudaEventSynchronize(up_ev[b]);                          // the DMA out of this bounce buffer (chunk ci-NB) is done
             }
             uint8_t* hb = static_cast<uint8_t*>(c->h_bounce[b]);
             for (int t = 0; t < n_taxa; ++t) memcpy(hb + (size_t)t * m, src + (size_t)t * pitch, (size_t)m);
             src = hb;
             src_pitch = m;
         }
+        SR_PIPE_EV(h0, c->s_h2d);
         cudaError_t e = cudaMemcpy2DAsync(c->d_chunk_states[b].p, cpitch, src, src_pitch, m, n_taxa, cudaMemcpyHostToDevice, c->s_h2d);
         if (e != cudaSuccess) { rc = fail(c, SR_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
         if (c->input_chars) encode_chars_kernel<<<c->n_sm * 4, 256, 0, c->s_h2d>>>(c->d_chunk_states[b].as<uint4>(), ((size_t)cpitch * n_taxa + 512) / 16);
         else sanitize_kernel<<<c->n_sm * 4, 256, 0, c->s_h2d>>>(c->d_chunk_states[b].as<uint4>(), ((size_t)cpitch * n_taxa + 512) / 16);
         cudaEventRecord(up_ev[b], c->s_h2d);
+        SR_PIPE_EV(h1, c->s_h2d);
         cudaStreamWaitEvent(c->stream, up_ev[b], 0);
-        if (ci >= 2) cudaStreamWaitEvent(c->stream, free_ev[b], 0);     // output buffers b drained
+        if (ci >= NB) cudaStreamWaitEvent(c->stream, free_ev[b], 0);    // output buffers b drained
+        SR_PIPE_EV(k0, c->stream);
         rc = run_block(c, c->stream, c->d_chunk_states[b].as<uint8_t>(), cpitch, n_taxa, 0, m, c->d_chunk_lnl[b].as<double>(),
                        joint ? c->d_chunk_joint[b].as<double>() : nullptr, compact ? c->d_chunk_compact[b].p : nullptr, threshold, 0);
         if (rc) break;
         cudaEventRecord(done_ev[b], c->stream);
         cudaEventRecord(sfree_ev[b], c->stream);
+        SR_PIPE_EV(k1, c->stream);
         cudaStreamWaitEvent(c->s_d2h, done_ev[b], 0);
+        SR_PIPE_EV(d0, c->s_d2h);
         if ((rc = d2h(c, c->s_d2h, done_ev[b], pin_lnl, lnl + done, c->d_chunk_lnl[b].p, sizeof(double) * m))) break;
         if (joint && (rc = d2h(c, c->s_d2h, done_ev[b], pin_joint, joint + done * 400, c->d_chunk_joint[b].p, sizeof(double) * 400 * m))) break;
         if (compact && (rc = d2h(c, c->s_d2h, done_ev[b], pin_compact, compact + done, c->d_chunk_compact[b].p, sizeof(sr_compact) * m))) break;
         cudaEventRecord(free_ev[b], c->s_d2h);
+        SR_PIPE_EV(d1, c->s_d2h);
+        tl_set_m(ci, m);
         done += m;
     }
     cudaError_t e0 = cudaStreamSynchronize(c->s_h2d), e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_d2h);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(up_ev[i]); cudaEventDestroy(done_ev[i]); cudaEventDestroy(free_ev[i]); cudaEventDestroy(sfree_ev[i]); }
+#ifdef SR_TIMELINE
+    if (getenv("SR_PIPE_DUMP")) {
+        for (size_t i = 0; i < tl.size(); ++i) {
+            float t[6];
+            cudaEvent_t evs[6] = {tl[i].h0, tl[i].h1, tl[i].k0, tl[i].k1, tl[i].d0, tl[i].d1};
+            for (int j = 0; j < 6; ++j) cudaEventElapsedTime(&t[j], tl[0].h0, evs[j]);
+            fprintf(stderr, "chunk %2zu cols %7lld | h2d %7.2f-%7.2f | kernels %7.2f-%7.2f | d2h %7.2f-%7.2f\n", i, (long long)tl[i].m, t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+    }
+    for (auto& e : tl) { cudaEventDestroy(e.h0); cudaEventDestroy(e.h1); cudaEventDestroy(e.k0); cudaEventDestroy(e.k1); cudaEventDestroy(e.d0); cudaEventDestroy(e.d1); }
+#endif
+    for (int i = 0; i < NB; ++i) { cudaEventDestroy(up_ev[i]); cudaEventDestroy(done_ev[i]); cudaEventDestroy(free_ev[i]); cudaEventDestroy(sfree_ev[i]); }
     if (rc) return rc;
     if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
         cudaGetLastError();

@@ -319,9 +319,9 @@ def test_ragged_offsets_and_chunks(ctx, example_problem):
     assert rel_err(one["lnl"], np.tile(lnl, 9)) < TOL
     # the streamed pipeline's ramp of short chunks at both ends (needs >= 8 kernel waves per chunk to engage) and an
     # odd-sized middle remainder: same bits as uniform chunks and as the resident path
-    wide = np.tile(p.states, (1, 1201))[:, :156001]
+    wide = np.tile(p.states, (1, 1901))[:, :247001]
     try:
-        ctx.set_option("stream_chunk_cols", 53000)
+        ctx.set_option("stream_chunk_cols", 60000)
         tapered = ctx.run_streamed(wide, want_joint=True, want_compact=True, threshold=0.3)
         ctx.set_option("stream_taper", 0)
         uniform = ctx.run_streamed(wide, want_joint=True, want_compact=True, threshold=0.3)
