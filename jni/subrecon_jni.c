@@ -66,6 +66,15 @@ JNIEXPORT jint JNICALL Java_subrecon_recon_NativeRecon_runStreamed(JNIEnv *env, 
     return sr_run_streamed(CTX(ctx), nTaxa, nSites, st, pitch, site0, n, l, j, NULL, 0.5);
 }
 
+/* sr_set_option: "input_chars", "cherry_tables", "compress_patterns", ... (include/subrecon_b200.h) */
+JNIEXPORT jint JNICALL Java_subrecon_recon_NativeRecon_setOption(JNIEnv *env, jclass cls, jlong ctx, jstring name, jlong value) {
+    const char *n = (*env)->GetStringUTFChars(env, name, NULL);
+    if (!n) return SR_ERR_OOM;
+    const int rc = sr_set_option(CTX(ctx), n, (int64_t)value);
+    (*env)->ReleaseStringUTFChars(env, name, n);
+    return rc;
+}
+
 JNIEXPORT jobject JNICALL Java_subrecon_recon_NativeRecon_hostAlloc(JNIEnv *env, jclass cls, jlong bytes) {
     void *p = sr_host_alloc((size_t)bytes);
     return p ? (*env)->NewDirectByteBuffer(env, p, bytes) : NULL;
