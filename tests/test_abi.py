@@ -56,3 +56,13 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "libsubrecon_oracle" not in src, f
+
+
+def test_jni_shim_compiles_against_the_abi():
+    """No JDK in this image: the shim (jni/subrecon_jni.c) is compiled with -fsyntax-only against a minimal mock of
+    <jni.h> (tests/cpp/jni_mock/jni.h), which checks every sr_* call in it against include/subrecon_b200.h."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-fsyntax-only",
+                           "-I", os.path.join(root, "tests", "cpp", "jni_mock"), "-I", os.path.join(root, "include"),
+                           os.path.join(root, "jni", "subrecon_jni.c")])
