@@ -48,7 +48,6 @@ def parse_args():
     ap.add_argument("--model", default="wag")
     ap.add_argument("--ncat", type=int, default=4)
     ap.add_argument("--alpha", type=float, default=0.5)
-    ap.add_argument("--tile-m", type=int, default=0, help="0 = library default")
     ap.add_argument("--chunk-cols", type=int, default=0, help="0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -204,8 +203,6 @@ def run_b200(a):
     tree, flat, model, rates, base = make_problem(a, seed_shift=rank)
     L, N = a.columns, base.shape[0]
     ctx = native.Context(local)
-    if a.tile_m:
-        ctx.set_option("tile_m", a.tile_m)
     if a.chunk_cols:
         ctx.set_option("chunk_cols", a.chunk_cols)
     ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)

@@ -40,17 +40,33 @@ typedef enum {
 typedef struct sr_ctx sr_ctx;
 
 /* One compacted column: what SiteResult's constructor scan extracts from the 400 probabilities
- * (recon/SiteResult.java:69-83) plus the print decision of SubRecon.java:138. */
+ * (recon/SiteResult.java:69-83) plus the print decision of SubRecon.java:138 — everything the reference keeps of a
+ * column (it deliberately drops the 20x20 matrix, SiteResult.java:55). This is the result path to use whenever the
+ * caller is going to build SiteResults: 112 bytes per column instead of 3 208.
+ *
+ * LOSSLESS BY CONSTRUCTION: the 400 probabilities sum to 1, so at most floor(1/threshold) of them can be >= threshold
+ * (2 at the reference's default -threshold 0.5). A record holds `compact_cap` entries (option, default SR_COMPACT_MAX
+ * = 8, i.e. every threshold >= 0.125); sr_run* REFUSE (SR_ERR_ARG) a threshold whose floor(1/threshold) exceeds the
+ * capacity instead of truncating. For smaller thresholds raise the capacity — sr_set_option("compact_cap", c) with
+ * c = sr_compact_cap_for(threshold), up to 400 — and step through the output with sr_compact_stride(c):
+ *     record = { lnl, max_ii_prob, max_prob, n_kept, interesting }            32 bytes
+ *              int16 pair[c]   (padded to a multiple of 8 bytes)
+ *              double prob[c]
+ * `sr_compact` below is exactly that layout for c = SR_COMPACT_MAX. */
 #define SR_COMPACT_MAX 8
 typedef struct {
     double  lnl;                    /* marginal site log-likelihood (SiteResult.getMarginalLnL)        */
     double  max_ii_prob;            /* largest diagonal entry   (SiteResult.getMaxIIProb)             */
     double  max_prob;               /* largest entry            (SiteResult.getMaxProb)               */
-    int32_t n_kept;                 /* number of entries >= threshold (may exceed SR_COMPACT_MAX)      */
+    int32_t n_kept;                 /* number of entries >= threshold                                  */
     int32_t interesting;            /* maxII <= 1-threshold && maxProb >= threshold (SubRecon.java:138) */
-    int16_t pair[SR_COMPACT_MAX];   /* a*20+b of the first SR_COMPACT_MAX kept entries, canonical order */
+    int16_t pair[SR_COMPACT_MAX];   /* a*20+b of the kept entries in the reference's scan order (a-major); -1 = unused */
     double  prob[SR_COMPACT_MAX];
 } sr_compact;
+/* Entries a record must hold for `threshold` to be lossless: min(400, floor(1/threshold)); 400 for threshold <= 0. */
+int sr_compact_cap_for(double threshold);
+/* Bytes per record of capacity `cap` (1..400): 32 + round_up(2*cap, 8) + 8*cap; sizeof(sr_compact) for cap = 8. */
+size_t sr_compact_stride(int cap);
 
 /* Per-kernel device timings accumulated since the last sr_profile_reset (CUDA events on the
  * launching stream). ms_* are sums over launches. */
@@ -66,6 +82,27 @@ typedef struct {
 int sr_create(sr_ctx **out, int device);
 void sr_destroy(sr_ctx *ctx);
 const char *sr_last_error(const sr_ctx *ctx);   /* ctx may be NULL: error of the failed sr_create */
+
+/* The same for a whole box from ONE host process (the reference is a single JVM, SubRecon.java:93): n_dev contexts, one
+ * per GPU (dev_ids NULL = devices 0..n_dev-1; n_dev <= 0 = every visible device), each driven by its own host thread
+ * inside the calls below. Columns are independent (SubRecon.java:112-116), so sr_multi_run_streamed hands device g the
+ * contiguous block [g*ceil(n/G), ...) of the column range and the blocks' results land in the caller's arrays in place:
+ * no inter-GPU traffic at all. The setters broadcast to every context. Host buffers should come from sr_host_alloc
+ * (page-locked for every device). Not thread-safe; one sr_multi per caller thread. */
+typedef struct sr_multi sr_multi;
+int sr_multi_create(sr_multi **out, int n_dev, const int *dev_ids);
+void sr_multi_destroy(sr_multi *m);
+const char *sr_multi_last_error(const sr_multi *m);            /* m may be NULL: error of the failed sr_multi_create */
+int sr_multi_count(const sr_multi *m);
+sr_ctx *sr_multi_ctx(sr_multi *m, int i);                      /* context i, e.g. for sr_get_profile / sr_schedule_info */
+int sr_multi_set_model(sr_multi *m, const double eval[20], const double evec[400], const double ievc[400], const double pi[20]);
+int sr_multi_set_rates(sr_multi *m, int K, const double *rates);
+int sr_multi_set_tree(sr_multi *m, int32_t n_nodes, const int32_t *child_off, const int32_t *child_idx,
+                      const double *blen, const int32_t *leaf_row, int32_t root);
+int sr_multi_set_option(sr_multi *m, const char *name, int64_t value);
+/* Replaces the submit/join loop (SubRecon.java:112-142) on all GPUs of the box; arguments as sr_run_streamed. */
+int sr_multi_run_streamed(sr_multi *m, int32_t n_taxa, int64_t n_sites, const uint8_t *states, int64_t pitch,
+                          int64_t site0, int64_t n, double *lnl, double *joint, sr_compact *compact, double threshold);
 
 /* Replaces the model argument of the task constructor (recon/JointBranchReconstruction.java:49-56):
  * the eigensystem PAL holds in MatrixExponential.{Eval,Evec,Ievc} after any setDistance call
@@ -93,7 +130,8 @@ int sr_set_alignment(sr_ctx *ctx, int32_t n_taxa, int64_t n_sites, const uint8_t
 
 /* Replaces the submit/join loop (SubRecon.java:112-142) for columns [site0, site0+n) of the resident
  * alignment. lnl[n]; joint[n*400] (a*20+b, a = state at root child 0, b = at root child 1) or NULL;
- * compact[n] or NULL (filled with `threshold`). Host buffers; pinned ones (sr_host_alloc) are DMA'd directly. */
+ * compact[n] or NULL (filled with `threshold`; records of sr_compact_stride(compact_cap) bytes — SR_ERR_ARG if that
+ * capacity could truncate at this threshold, see sr_compact). Host buffers; pinned ones (sr_host_alloc) are DMA'd directly. */
 int sr_run(sr_ctx *ctx, int64_t site0, int64_t n, double *lnl, double *joint, sr_compact *compact,
            double threshold);
 
@@ -103,45 +141,54 @@ int sr_run_device(sr_ctx *ctx, int64_t site0, int64_t n, double *d_lnl, double *
                   double threshold, void *stream);
 
 /* End-to-end variant: the alignment stays in HOST memory (states[taxon*pitch + site]); column chunks are
- * uploaded, computed and downloaded in a double-buffered pipeline. Nothing needs to be resident. */
+ * uploaded, computed and downloaded in a three-stage pipeline (three buffers per stage). Nothing needs to be resident. */
 int sr_run_streamed(sr_ctx *ctx, int32_t n_taxa, int64_t n_sites, const uint8_t *states, int64_t pitch,
                     int64_t site0, int64_t n, double *lnl, double *joint, sr_compact *compact, double threshold);
 
-/* Pinned host memory for the buffers above (JNI: wrap in a direct ByteBuffer). */
+/* Pinned host memory for the buffers above, page-locked for every device (JNI: wrap in a direct ByteBuffer). */
 void *sr_host_alloc(size_t bytes);
 void sr_host_free(void *p);
 
-/* Tuning / introspection. Options: "tile_m" (MMA column tiles per warp: 2 or 4), "warps" (consumer warps per CTA: 12 =
- * default, on re-allocated registers; 8, 11, 15 = tuning variants), "realloc" (0/1: producer warp on re-allocated
- * registers (setmaxnreg), 12 x tile_m 2 or 8 x tile_m 4 consumer warps), "holes" (pauses inside a warp's MMA burst: 0, 1, 2
- * or the digits of the k-steps to pause before), "rotate" (0/1 burst hand-off between the warps of an SM sub-partition),
- * "compress_patterns" (0/1: compute each distinct column pattern of a batch once and copy the result to its
- * duplicates; off by default), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage),
+/* Tuning / introspection. Options: "compact_cap" (entries per compact record, 1..400, default 8; see sr_compact),
+ * "strict_root" (0/1, default 0: reject, with SR_ERR_UNSUPPORTED from sr_set_tree / sr_set_rates, a tree whose root has a
+ * tip as child when K > 1 — the reference throws on every column of such input, utils/Utils.java:56-70; off = return the
+ * well-defined limit), "compress_patterns" (0/1: compute each distinct column pattern of a batch once and copy the result
+ * to its duplicates; off by default), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage),
  * "stream_taper" (0/1: short pipeline chunks at both ends of a streamed run, on by default), "input_chars" (0/1:
  * alignment bytes are residue letters, see sr_set_alignment), "cherry_tables" (0/1, default 1: tabulate every cherry's
  * contribution per state pair once per rate class and gather it instead of contracting it per column) with
- * "cherry_table_mb" (memory cap, default 4096), "cherry_pairs" (0/1, default 1: a step may gather two such clades) and
- * "cherry_pitchforks" (0/1, default 1: the same one level up, a cherry plus a tip, 9261 state triples), "profile"
- * (0/1: record per-kernel events), "rescale_every" (edges between power-of-two rescalings, default 8). */
+ * "cherry_table_mb" (memory cap, default 4096), "cherry_pairs" (0/1, default 1: a step may gather several such clades) and
+ * "cherry_pitchforks" (0/1, default 1: the same one level up, a cherry plus a tip, 9261 state triples), "k_fastest" (0/1,
+ * default 0: work items ordered tile-major, i.e. the K rate classes of a column tile run concurrently and the states are read
+ * from HBM once instead of K times — but every rate class's clade tables are then hot at once and miss L2 more often;
+ * rate-major is 6 % faster at BASELINE config #3 and HBM is at 1 % of its roof either way), "profile"
+ * (0/1: record per-kernel events), "rescale_every" (edges between power-of-two rescalings, 1..12, default 8). */
 int sr_set_option(sr_ctx *ctx, const char *name, int64_t value);
 int sr_get_profile(sr_ctx *ctx, sr_profile *out);     /* synchronises the context's streams */
 int sr_profile_reset(sr_ctx *ctx);
 /* Schedule facts for the current tree: number of pruning steps, stack depth needed, and the
  * algorithmic flops per column per rate class (820*E_int + 20*E_leaf + 1200). */
 int sr_schedule_info(sr_ctx *ctx, int64_t *n_steps, int32_t *stack_depth, double *flops_per_column_rate);
-/* Host-only (no GPU needed): the fused pruning schedule sr_set_tree would build. steps[12*i..] = {word, alignment row of
- * gather 0, 1, 2; second row of the step's first and second clade gather, their third rows; first table row of each, 0, 0};
- * word bits: 0-1 MV (1 = A=P·A,
- * 2 = A=pop∘P·A), 2-3 number of tip gathers before the MV, 4 first gather starts a new partial, 5 one tip gather after
- * the MV, 6 rescale, 7 push, 8/9 store as root child A/B, 10-11 and 12-13 positions (1-based, among the step's gathers) of
- * up to two collapsed-clade gathers, 14 / 15 the first / second of them is a pitchfork (three tips).
+/* Host-only (no GPU needed): the fused pruning schedule sr_set_tree would build. steps[16*i..] = {word, alignment row of
+ * gather 0, 1, 2; for a clade gather g its second row (4+g), its third row (7+g) and its table's first row (10+g); 3 unused};
+ * word bits: 0-1 MV (1 = R = P·A, 2 = R = pop ∘ P·A), 2-3 number of gathers before the MV, 4 first gather starts a new
+ * partial, 5 one gather after the MV, 6 rescale, 7 push, 8/9 store as root child A/B, 10-12 gather g reads a collapsed
+ * clade's table, 13-15 that clade is a pitchfork (three tips).
  * node_slot[v] = position of node v's parent edge in the matrix stream (per step: MV first, then tips), -1 if it has
  * none, -2-c if v is the top of collapsed clade c (a cherry: two tip children; or a pitchfork: a cherry and a tip — with
  * `cherry_tables` its contribution to its parent is tabulated per state combination and gathered like a tip's).
+ * The arrays are validated exactly as sr_set_tree validates them (one parent per node, no cycle, ...).
  * This replaces the recursion order of downTreeMarginal (JointBranchReconstruction.java:191-247). */
 int sr_schedule_dump(int32_t n_nodes, const int32_t *child_off, const int32_t *child_idx, const double *blen,
                      const int32_t *leaf_row, int32_t root, int32_t rescale_every, int32_t cherry_tables, int64_t cap_steps,
                      int32_t *steps, int32_t *node_slot, int64_t *n_steps, int32_t *stack_depth);
+/* Host-only: the same schedule as the two record streams the pruning kernel reads (subrecon_b200/csrc/prune.cuh):
+ * crec[4*i..] for the consumer warps, prec[8*i..] for the TMA producer, clade_gathers[4*j..] = {row a, row b, row c or -1, 0}
+ * for the index pre-pass; capacity cap_steps steps and 3*cap_steps clade gathers. tests/test_schedule.py interprets them on
+ * the CPU against the oracle. */
+int sr_schedule_records(int32_t n_nodes, const int32_t *child_off, const int32_t *child_idx, const double *blen,
+                        const int32_t *leaf_row, int32_t root, int32_t rescale_every, int32_t cherry_tables, int64_t cap_steps,
+                        uint32_t *crec, uint32_t *prec, int32_t *clade_gathers, int64_t *n_steps, int64_t *n_clade_gathers);
 /* Live FP64 roofline probe: runs a register-resident DMMA (mma.sync m8n8k4 f64) loop for ~`ms` and
  * returns TFLOP/s — the denominator bench.py reports the pruning kernel against. */
 int sr_measure_fp64_peak(sr_ctx *ctx, double ms, double *tflops);

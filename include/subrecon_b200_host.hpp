@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -99,15 +100,26 @@ public:
             }
         if (sortByProb) sortByProbImpl();
     }
-    // from one sr_compact record (device-side scan); throws if more entries passed the threshold than the record keeps
-    SiteResult(int site, const sr_compact& c, bool sortByProb = true, int sigDigits = Constants::DEFAULT_SIG_DIGITS)
-        : site_(site), marginalLnL_(c.lnl), maxIIProb_(c.max_ii_prob), maxProb_(c.max_prob), sigDigits_(sigDigits) {
-        if (c.n_kept > SR_COMPACT_MAX) throw std::runtime_error("sr_compact overflow: rerun with the full joint output");
-        for (int i = 0; i < c.n_kept; ++i) {
-            aboveThreshProbs_.push_back(c.prob[i]);
-            aboveThreshSubs_.push_back(std::string{Constants::AA_ORDER[c.pair[i] / 20], Constants::AA_ORDER[c.pair[i] % 20]});
+    // From one compact record (device-side scan, sr_compact layout of capacity `cap`), the way the Java host does it
+    // (java/subrecon/recon/NativeRecon.java::reconstruct): through the constructor above, on a matrix that holds the kept
+    // entries plus carriers for maxIIProb / maxProb when those are below the threshold.
+    static SiteResult fromCompact(int site, const unsigned char* rec, int cap, double threshold, bool sortByProb = true,
+                                  int sigDigits = Constants::DEFAULT_SIG_DIGITS) {
+        double lnl, maxII, maxP;
+        int32_t kept;
+        std::memcpy(&lnl, rec, 8); std::memcpy(&maxII, rec + 8, 8); std::memcpy(&maxP, rec + 16, 8); std::memcpy(&kept, rec + 24, 4);
+        if (kept > cap) throw std::runtime_error("compact record overflow");
+        const unsigned char* pairs = rec + 32;
+        const unsigned char* probs = rec + 32 + (2 * cap + 7) / 8 * 8;
+        double m[400] = {0.0};
+        for (int k = 0; k < kept; ++k) {
+            int16_t ab; double pr;
+            std::memcpy(&ab, pairs + 2 * k, 2); std::memcpy(&pr, probs + 8 * k, 8);
+            m[ab] = pr;
         }
-        if (sortByProb) sortByProbImpl();
+        if (maxII < threshold) m[0] = std::fmax(m[0], maxII);
+        if (maxP < threshold && maxP > maxII) m[1] = std::fmax(m[1], maxP);
+        return SiteResult(site, lnl, m, threshold, sortByProb, sigDigits);
     }
     int getSite() const { return site_; }
     double getMarginalLnL() const { return marginalLnL_; }
@@ -157,7 +169,8 @@ struct Tree {
 struct Alignment {
     int32_t nTaxa = 0;
     int64_t nSites = 0;
-    std::vector<uint8_t> states;                        // [taxon][site], 0..19 or SR_STATE_MISSING
+    std::vector<uint8_t> states;                        // [taxon][site], 0..19 or SR_STATE_MISSING — or, with `letters`, the
+    bool letters = false;                               // residue characters themselves (translated on the device)
 };
 struct Model {                                          // PAL MatrixExponential.{Eval,Evec,Ievc}
     double Eval[20], Evec[400], Ievc[400];
@@ -165,58 +178,95 @@ struct Model {                                          // PAL MatrixExponential
 
 class JointBranchReconstruction {
 public:
+    static constexpr int MAX_COMPACT_CAP = 64;     // above this many kept entries per column the full matrix is the smaller result
     // JointBranchReconstruction(alignment, tree, model, pi, logPi, rateDist, threshold, sigDigits, sortByProb, sanityCheck, site)
-    // — logPi is derived on the device; `site` becomes the (site0, n) range of call().
+    // — logPi is derived on the device; `site` becomes the (site0, n) range of call(). The call sequence below is the
+    // Java host's (java/subrecon/recon/NativeRecon.java + java/SubRecon.run.patch.java), statement for statement:
+    // sr_multi_create, "strict_root", set_model, set_rates, set_tree, then per call "input_chars" / "compact_cap",
+    // sr_host_alloc'ed buffers and sr_multi_run_streamed.
     JointBranchReconstruction(const Alignment& alignment, const Tree& tree, const Model& model, const double pi[20],
                               const std::vector<double>& rates, double threshold = Constants::DEFAULT_PRINT_THRESHOLD,
                               int sigDigits = Constants::DEFAULT_SIG_DIGITS, bool sortByProb = true,
-                              bool sanityCheck = false, int device = 0)
+                              bool sanityCheck = false, int nDevices = 1)
         : threshold_(threshold), sigDigits_(sigDigits), sortByProb_(sortByProb), sanityCheck_(sanityCheck),
-          nSites_(alignment.nSites) {
-        if (sr_create(&ctx_, device) != SR_OK) throw std::runtime_error(sr_last_error(nullptr));
+          nTaxa_(alignment.nTaxa), nSites_(alignment.nSites), letters_(alignment.letters) {
+        if (sr_multi_create(&m_, nDevices, nullptr) != SR_OK) throw std::runtime_error(sr_multi_last_error(nullptr));
         try {
-            ck(sr_set_model(ctx_, model.Eval, model.Evec, model.Ievc, pi));
-            ck(sr_set_rates(ctx_, (int)rates.size(), rates.data()));
-            ck(sr_set_tree(ctx_, tree.nNodes, tree.childOff.data(), tree.childIdx.data(), tree.branchLength.data(),
-                           tree.leafRow.data(), tree.root));
-            ck(sr_set_alignment(ctx_, alignment.nTaxa, alignment.nSites, alignment.states.data(), alignment.nSites));
+            ck(sr_multi_set_option(m_, "strict_root", 1));
+            ck(sr_multi_set_model(m_, model.Eval, model.Evec, model.Ievc, pi));
+            ck(sr_multi_set_rates(m_, (int)rates.size(), rates.data()));
+            ck(sr_multi_set_tree(m_, tree.nNodes, tree.childOff.data(), tree.childIdx.data(), tree.branchLength.data(),
+                                 tree.leafRow.data(), tree.root));
+            const size_t bytes = (size_t)alignment.nTaxa * (size_t)alignment.nSites;
+            states_ = static_cast<uint8_t*>(sr_host_alloc(bytes));                   // NativeRecon.pinnedLetters
+            if (!states_) throw std::runtime_error("sr_host_alloc failed");
+            std::memcpy(states_, alignment.states.data(), bytes);
         } catch (...) {
-            sr_destroy(ctx_);
+            sr_host_free(states_);
+            sr_multi_destroy(m_);
             throw;
         }
     }
     JointBranchReconstruction(const JointBranchReconstruction&) = delete;
     JointBranchReconstruction& operator=(const JointBranchReconstruction&) = delete;
-    ~JointBranchReconstruction() { sr_destroy(ctx_); }
+    ~JointBranchReconstruction() { sr_host_free(states_); sr_multi_destroy(m_); }
 
     // Callable.call() for every column in [site0, site0 + n): results in column order (Future.get(), SubRecon.java:123-126)
     std::vector<SiteResult> call(int64_t site0 = 0, int64_t n = -1) {
         if (n < 0) n = nSites_ - site0;
-        std::vector<double> lnl((size_t)n), joint((size_t)n * 400);
-        ck(sr_run(ctx_, site0, n, lnl.data(), joint.data(), nullptr, threshold_));
+        ck(sr_multi_set_option(m_, "input_chars", letters_ ? 1 : 0));
+        const int cap = sr_compact_cap_for(threshold_);
+        const bool useCompact = cap <= MAX_COMPACT_CAP && !sanityCheck_;             // -debug sums all 400 entries
+        double* lnl = static_cast<double*>(sr_host_alloc(sizeof(double) * (size_t)n));
+        double* joint = nullptr;
+        unsigned char* compact = nullptr;
+        size_t stride = 0;
         std::vector<SiteResult> out;
-        out.reserve((size_t)n);
-        for (int64_t i = 0; i < n; ++i) {
-            const double* p = joint.data() + (size_t)i * 400;
-            if (sanityCheck_) {                                              // checkSumToOne, JointBranchReconstruction.java:157-166
-                double sum = 0.0;
-                for (int e = 0; e < 400; ++e) sum += p[e];
-                if (sum < 1.0 - Constants::EPSILON || sum > 1.0 + Constants::EPSILON)
-                    throw std::runtime_error("ERROR: Failed sanity check. Sum of posterior probs != 1.0. sum=" + javaDoubleToString(sum));
+        try {
+            if (useCompact) {
+                ck(sr_multi_set_option(m_, "compact_cap", cap));
+                stride = sr_compact_stride(cap);
+                compact = static_cast<unsigned char*>(sr_host_alloc(stride * (size_t)n));
+            } else {
+                joint = static_cast<double*>(sr_host_alloc(sizeof(double) * 400 * (size_t)n));
             }
-            out.emplace_back((int)(site0 + i), lnl[(size_t)i], p, threshold_, sortByProb_, sigDigits_);
+            if (!lnl || !(useCompact ? (void*)compact : (void*)joint)) throw std::runtime_error("sr_host_alloc failed");
+            ck(sr_multi_run_streamed(m_, nTaxa_, nSites_, states_, nSites_, site0, n, lnl, joint,
+                                     reinterpret_cast<sr_compact*>(compact), threshold_));
+            out.reserve((size_t)n);
+            for (int64_t i = 0; i < n; ++i) {
+                if (useCompact) {
+                    out.push_back(SiteResult::fromCompact((int)(site0 + i), compact + stride * (size_t)i, cap, threshold_, sortByProb_, sigDigits_));
+                    continue;
+                }
+                const double* p = joint + (size_t)i * 400;
+                if (sanityCheck_) {                                          // checkSumToOne, JointBranchReconstruction.java:157-166
+                    double sum = 0.0;
+                    for (int e = 0; e < 400; ++e) sum += p[e];
+                    if (sum < 1.0 - Constants::EPSILON || sum > 1.0 + Constants::EPSILON)
+                        throw std::runtime_error("ERROR: Failed sanity check. Sum of posterior probs != 1.0. sum=" + javaDoubleToString(sum));
+                }
+                out.emplace_back((int)(site0 + i), lnl[(size_t)i], p, threshold_, sortByProb_, sigDigits_);
+            }
+        } catch (...) {
+            sr_host_free(lnl); sr_host_free(joint); sr_host_free(compact);
+            throw;
         }
+        sr_host_free(lnl); sr_host_free(joint); sr_host_free(compact);
         return out;
     }
-    sr_ctx* context() { return ctx_; }
+    sr_multi* contexts() { return m_; }
 
 private:
-    void ck(int rc) { if (rc != SR_OK) throw std::runtime_error(sr_last_error(ctx_)); }
-    sr_ctx* ctx_ = nullptr;
+    void ck(int rc) { if (rc != SR_OK) throw std::runtime_error(sr_multi_last_error(m_)); }
+    sr_multi* m_ = nullptr;
+    uint8_t* states_ = nullptr;
     double threshold_;
     int sigDigits_;
     bool sortByProb_, sanityCheck_;
+    int32_t nTaxa_;
     int64_t nSites_;
+    bool letters_;
 };
 
 // The ordered join + print loop of SubRecon.run() (SubRecon.java:122-150); returns the stdout lines.

@@ -5,7 +5,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/subrecon_b200.h"
@@ -14,7 +17,7 @@
 
 using namespace srk;
 
-static_assert(sizeof(sr_compact) == sizeof(CompactRec), "sr_compact layout");
+static_assert(sizeof(sr_compact) == sizeof(CompactRec) && compact_stride(SR_COMPACT_MAX) == sizeof(sr_compact), "sr_compact layout");
 
 namespace {
 
@@ -46,6 +49,7 @@ struct sr_ctx {
     int max_smem = 0;
     std::string err;
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_up[3] = {}, ev_done[3] = {}, ev_free[3] = {}, ev_sfree[3] = {};   // pipeline hand-offs, created once
 
     // model / rates
     bool has_model = false, has_rates = false, has_tree = false, has_aln = false;
@@ -57,8 +61,11 @@ struct sr_ctx {
     int32_t n_nodes = 0, root = 0;
     std::vector<int32_t> child_off, child_idx, leaf_row;
     std::vector<double> blen;
-    std::vector<int32_t> steps;         // fused schedule: 4 ints per step {word, leaf row 0, 1, 2}
+    std::vector<int32_t> steps;         // fused schedule: STEP_INTS ints per step (see sr_schedule_dump)
     std::vector<int32_t> step_off;      // per step: offset (doubles) of its matrices in a rate class's stream
+    std::vector<uint32_t> crec, prec;   // what the kernel reads: 4 words per step for the consumers, 8 for the producer (prune.cuh)
+    std::vector<int32_t> clade_gathers; // per clade gather of the schedule, in order: {row a, row b, row c or -1, 0} (K0b)
+    std::vector<int32_t> shape_hist;    // steps per consumer shape id (introspection)
     std::vector<int32_t> slot_kind, slot_off;   // per edge: layout kind + offset (doubles)
     std::vector<double> slot_blen;
     std::vector<int32_t> node_slot;     // node -> slot that applies its parent edge (-1: none)
@@ -81,19 +88,17 @@ struct sr_ctx {
 #endif
 
     // options
-    int tile_m = 2;
-    int debug = 0;
-    int holes = 2;                      // pauses inside a warp's MMA burst (0..2), see kernels.cuh
     int cherry_pairs = 1;               // let one step gather two cherries (siblings): trees with many cherry pairs
-    bool has_pairs = false;             // the current schedule contains such steps (selects the kernel variant)
+    int debug = 0;
+    int k_fastest = 0;                  // work items tile-major (the K rate classes of a tile run concurrently) instead of rate-major
+    int strict_root = 0;                // reject a tip as root child when K > 1 (the reference fails every column there)
+    int compact_cap = SR_COMPACT_MAX;   // entries kept per compact record
     int cherry_pitchforks = 1;          // also tabulate (cherry, tip) clades: 9261 rows each
     int cherry_tables = 1;              // collapse cherries into 441-row lookup tables (see build_schedule)
     int64_t cherry_table_mb = 4096;     // memory cap for those tables; clades beyond it are pruned the ordinary way
     bool input_chars = false;           // alignment bytes are residue letters, translated on the device
     int compress = 0;                   // reduce every batch to its distinct column patterns first
     int rotate = 1;                     // named-barrier burst rotation among the warps of an SM sub-partition
-    int warps = 12;                     // consumer warps per CTA (tile_m == 2: 8, 11, 12 or 15)
-    bool realloc = true;                // producer warp on re-allocated registers (setmaxnreg): 12 x tile_m 2 or 8 x tile_m 4 consumers
     int64_t chunk_cols = 1 << 20;       // resident runs: columns per launch
     bool stream_taper = true;            // streamed runs: short chunks at both ends of the pipeline
     int64_t stream_chunk_cols = 1 << 17; // streamed runs: columns per pipeline stage (H2D | kernels | D2H overlap)
@@ -101,7 +106,7 @@ struct sr_ctx {
     bool profile = false;
 
     // device state
-    DevBuf d_model, d_rates, d_steps, d_stepoff, d_slotkind, d_slotoff, d_slotblen, d_pstream, d_proot, d_states, d_rootpart, d_rootexp, d_spill;
+    DevBuf d_model, d_rates, d_crec, d_prec, d_cgathers, d_cidx, d_slotkind, d_slotoff, d_slotblen, d_pstream, d_proot, d_states, d_rootpart, d_rootexp, d_spill;
     DevBuf d_pat_keys[2], d_pat_idx[2], d_pat_h2, d_pat_head, d_pat_uid, d_pat_rep, d_pat_map, d_pat_tmp, d_pat_states, d_pat_lnl, d_pat_joint, d_pat_compact;
     int64_t last_unique = 0, last_total = 0;
     DevBuf d_chunk_states[3], d_chunk_lnl[3], d_chunk_joint[3], d_chunk_compact[3], d_peak;   // pipeline buffers (sr_run: 2, streamed: 3)
@@ -118,14 +123,32 @@ struct sr_ctx {
 
 namespace {
 
-int fail(sr_ctx* c, int code, const char* fmt, ...) {
+int fail(sr_ctx* c, int code, const char* fmt, ...) noexcept {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (c) c->err = buf; else g_create_error = buf;
+    try {
+        if (c) c->err = buf; else g_create_error = buf;
+    } catch (...) {
+    }
     return code;
+}
+
+// Nothing throws or aborts across the ABI (include/subrecon_b200.h): the host side uses std::vector / std::string, so
+// every exported function runs inside this fence.
+template <typename F>
+int guarded(sr_ctx* c, F&& f) noexcept {
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        return fail(c, SR_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(c, SR_ERR_ARG, "internal error: %s", e.what());
+    } catch (...) {
+        return fail(c, SR_ERR_ARG, "internal error");
+    }
 }
 
 #define CUDA_TRY(ctx, expr)                                                                          \
@@ -137,6 +160,91 @@ int fail(sr_ctx* c, int code, const char* fmt, ...) {
                         "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
         }                                                                                            \
     } while (0)
+
+// inside the pipeline loops: note the failure, leave the loop, let the common exit drain the streams
+#define CUDA_STEP(ctx, rcvar, expr)                                                                  \
+    {                                                                                                \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            cudaGetLastError();                                                                      \
+            rcvar = fail(ctx, SR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            break;                                                                                   \
+        }                                                                                            \
+    }
+
+// ------------------------------------------------------------------------------------------------
+// The schedule as the kernel reads it (prune.cuh): everything a step needs is decided here, once per tree — the shape
+// id that selects the specialised step body, the stack level a step pops from / pushes to (the walk is static, so the
+// kernel keeps no stack pointer), the byte offset of every gather's source, the bytes the producer copies.
+// ------------------------------------------------------------------------------------------------
+int build_records(sr_ctx* c) {
+    const int n_steps = (int)c->steps.size() / STEP_INTS;
+    c->crec.assign((size_t)n_steps * 4, 0u);
+    c->prec.assign((size_t)n_steps * 8, 0u);
+    c->clade_gathers.clear();
+    c->shape_hist.assign(8, 0);
+    int sp = 0;
+    for (int i = 0; i < n_steps; ++i) {
+        const int32_t* st = &c->steps[(size_t)i * STEP_INTS];
+        const int32_t w = st[0];
+        const int mv = w & ST_MV_MASK, n_pre = (w >> ST_NPRE_SHIFT) & 3, post = (w & ST_NPOST) ? 1 : 0;
+        const bool set0 = (w & ST_PRE0_SET) != 0;
+        const int n_g = n_pre + post;
+        uint32_t x = 0, off[3] = {0, 0, 0}, rows[3] = {0, 0, 0}, kinds = 0;
+        int tix = 0;
+        for (int g = 0; g < n_g; ++g) {
+            if ((w >> (ST_CLADE_SHIFT + g)) & 1) {
+                const bool tri = ((w >> (ST_TRI_SHIFT + g)) & 1) != 0;
+                const int64_t byte_off = (int64_t)st[10 + g] * CHERRY_ROW_DOUBLES * 8;
+                if (byte_off > (int64_t)UINT32_MAX - PITCHFORK_ROWS * CHERRY_ROW_DOUBLES * 8)
+                    return fail(c, SR_ERR_UNSUPPORTED, "clade tables too large for 32-bit byte offsets; lower cherry_table_mb");
+                x |= CR_CLADE0 << g;
+                kinds |= 1u << g;
+                off[g] = (uint32_t)byte_off;
+                rows[g] = (uint32_t)(c->clade_gathers.size() / 4);
+                const int32_t cg[4] = {st[1 + g], st[4 + g], tri ? st[7 + g] : -1, 0};
+                c->clade_gathers.insert(c->clade_gathers.end(), cg, cg + 4);
+            } else {
+                off[g] = (uint32_t)((mv ? FRAG_BYTES : 0) + tix * TABLE_BYTES);
+                rows[g] = (uint32_t)st[1 + g];
+                ++tix;
+            }
+        }
+        int shape = SH_GENERAL;
+        if (n_pre == 0 && mv == 1) shape = post ? SH_MV1_POST : SH_MV1;
+        else if (n_pre == 0 && mv == 2) shape = post ? SH_MV2_POST : SH_MV2;
+        else if (n_pre == 2 && set0 && mv == 1) shape = post ? SH_NEW2_MV1_POST : SH_NEW2_MV1;
+        else if (n_pre == 2 && set0 && mv == 2 && !post) shape = SH_NEW2_MV2;
+        x |= (uint32_t)shape;
+        ++c->shape_hist[shape];
+        if (w & STF_RESCALE) x |= CR_RESCALE;
+        if (mv == 2) {
+            if (sp <= 0) return fail(c, SR_ERR_UNSUPPORTED, "internal: schedule pops an empty stack at step %d", i);
+            --sp;
+            x |= (uint32_t)sp << CR_POP_SHIFT;
+        }
+        if (w & STF_PUSH) {
+            if (sp >= 31) return fail(c, SR_ERR_UNSUPPORTED, "tree needs more than 31 stacked partials");
+            x |= CR_PUSH | ((uint32_t)sp << CR_PUSH_SHIFT);
+            ++sp;
+        }
+        if (w & STF_STORE_A) x |= CR_STORE_A;
+        if (w & STF_STORE_B) x |= CR_STORE_B;
+        x |= (uint32_t)n_pre << CR_NPRE_SHIFT;
+        if (set0) x |= CR_PRE_SET;
+        x |= (uint32_t)mv << CR_MV_SHIFT;
+        if (post) x |= CR_POST;
+        uint32_t* cr = &c->crec[(size_t)i * 4];
+        cr[0] = x; cr[1] = off[0]; cr[2] = off[1]; cr[3] = off[2];
+        uint32_t* pr = &c->prec[(size_t)i * 8];
+        pr[0] = (uint32_t)((int64_t)c->step_off[i] * 8);
+        pr[1] = (uint32_t)((mv ? FRAG_BYTES : 0) + tix * TABLE_BYTES);
+        pr[2] = (uint32_t)n_g | (kinds << 2);
+        pr[3] = rows[0]; pr[4] = rows[1]; pr[5] = rows[2];
+    }
+    if ((int64_t)c->rate_stride * 8 > (int64_t)UINT32_MAX) return fail(c, SR_ERR_UNSUPPORTED, "tree too large for 32-bit matrix-stream offsets");
+    return SR_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Pruning schedule. The reference recurses (JointBranchReconstruction.java:191-247); here the tree is
@@ -269,12 +377,9 @@ int build_schedule(sr_ctx* c) {
         c->cherry_blen.insert(c->cherry_blen.end(), lens, lens + 5);
     }
     if (c->ctab_rows > INT32_MAX) return fail(c, SR_ERR_UNSUPPORTED, "clade tables too large for 32-bit row offsets; lower cherry_table_mb");
-    // (two cherry gathers per step only for the default kernel layout: the tuning variants are single-gather builds)
-    const bool default_layout = c->tile_m == 2 && c->warps == 12 && c->realloc && c->holes == 2;
-    const int max_pseudo = (c->cherry_pairs && default_layout) ? 2 : 1;
+    const int max_pseudo = c->cherry_pairs ? 3 : 1;
     // ---- fuse into steps: [<=2 tip gathers] [one MV] [<=1 tip gather]; a push/store ends its step
     c->steps.clear(); c->step_off.clear();
-    c->has_pairs = false;
     c->slot_kind.clear(); c->slot_off.clear(); c->slot_blen.clear();
     c->node_slot.assign(n, -1);
     c->e_int = c->e_leaf = 0;
@@ -313,7 +418,7 @@ int build_schedule(sr_ctx* c) {
     };
     size_t i = 0;
     while (i < prims.size()) {
-        int32_t word = 0, rows[3] = {0, 0, 0}, row_b[2] = {0, 0}, row_c[2] = {0, 0}, row_off[2] = {0, 0};
+        int32_t word = 0, rows[3] = {0, 0, 0}, row_b[3] = {0, 0, 0}, row_c[3] = {0, 0, 0}, row_off[3] = {0, 0, 0};
         int n_leaf = 0, n_pre = 0;
         int n_pseudo = 0;                        // cherry-table gathers of this step (at most max_pseudo)
         auto is_pseudo = [&](const Prim& pr) { return pr.code <= P_LEAF_MUL && cherry_of[pr.child] >= 0; };
@@ -321,12 +426,13 @@ int build_schedule(sr_ctx* c) {
             if (is_pseudo(pr)) {
                 int rws[3];
                 const int nr = clade_rows(pr.child, rws);
-                rows[n_leaf++] = rws[0];
-                row_b[n_pseudo] = rws[1];
-                row_c[n_pseudo] = rws[2];
-                row_off[n_pseudo] = (int32_t)c->cherry_rowoff[cherry_of[pr.child]];
-                word |= n_leaf << (n_pseudo == 0 ? ST_PSEUDO_SHIFT : ST_PSEUDO2_SHIFT);
-                if (nr == 3) word |= (n_pseudo == 0 ? ST_PSEUDO_TRI : ST_PSEUDO2_TRI);
+                rows[n_leaf] = rws[0];
+                row_b[n_leaf] = rws[1];
+                row_c[n_leaf] = rws[2];
+                row_off[n_leaf] = (int32_t)c->cherry_rowoff[cherry_of[pr.child]];
+                word |= 1 << (ST_CLADE_SHIFT + n_leaf);
+                if (nr == 3) word |= 1 << (ST_TRI_SHIFT + n_leaf);
+                ++n_leaf;
                 ++n_pseudo;
                 s_cur += nr - 1;                 // two or three edges deep
             } else {
@@ -383,9 +489,10 @@ int build_schedule(sr_ctx* c) {
         if (last->store_b) word |= STF_STORE_B;
         c->steps.push_back(word);
         c->steps.push_back(rows[0]); c->steps.push_back(rows[1]); c->steps.push_back(rows[2]);
-        c->steps.push_back(row_b[0]); c->steps.push_back(row_b[1]); c->steps.push_back(row_c[0]); c->steps.push_back(row_c[1]);
-        c->steps.push_back(row_off[0]); c->steps.push_back(row_off[1]); c->steps.push_back(0); c->steps.push_back(0);
-        if (n_pseudo > 1) c->has_pairs = true;
+        for (int g = 0; g < 3; ++g) c->steps.push_back(row_b[g]);
+        for (int g = 0; g < 3; ++g) c->steps.push_back(row_c[g]);
+        for (int g = 0; g < 3; ++g) c->steps.push_back(row_off[g]);
+        for (int g = 13; g < STEP_INTS; ++g) c->steps.push_back(0);
         if (off_d > INT32_MAX - 4096) return fail(c, SR_ERR_UNSUPPORTED, "tree too large for 32-bit matrix-stream offsets");
     }
     c->rate_stride = off_d;
@@ -393,7 +500,7 @@ int build_schedule(sr_ctx* c) {
     c->root_blen = c->blen[rc0] + c->blen[rc1];
     c->sched_dirty = false;
     c->p_dirty = true;
-    return SR_OK;
+    return build_records(c);
 }
 
 void prof_begin(sr_ctx* c, cudaStream_t s, int kind, int64_t cols) {
@@ -418,8 +525,10 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     const int n_steps = (int)c->steps.size() / STEP_INTS, n_slots = (int)c->slot_kind.size();
     CUDA_TRY(c, c->d_model.reserve(sizeof(double) * 840));
     CUDA_TRY(c, c->d_rates.reserve(sizeof(double) * c->K));
-    CUDA_TRY(c, c->d_steps.reserve(sizeof(int32_t) * STEP_INTS * n_steps));
-    CUDA_TRY(c, c->d_stepoff.reserve(sizeof(int32_t) * n_steps));
+    const int n_cg = (int)c->clade_gathers.size() / 4;
+    CUDA_TRY(c, c->d_crec.reserve(sizeof(uint32_t) * 4 * n_steps));
+    CUDA_TRY(c, c->d_prec.reserve(sizeof(uint32_t) * 8 * n_steps));
+    CUDA_TRY(c, c->d_cgathers.reserve(sizeof(int32_t) * 4 * std::max(1, n_cg)));
     CUDA_TRY(c, c->d_slotkind.reserve(sizeof(int32_t) * n_slots));
     CUDA_TRY(c, c->d_slotoff.reserve(sizeof(int32_t) * n_slots));
     CUDA_TRY(c, c->d_slotblen.reserve(sizeof(double) * n_slots));
@@ -432,8 +541,9 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     // it may return before the DMA has landed). The stream is drained before the staging arrays go out of scope.
     CUDA_TRY(c, cudaMemcpyAsync(c->d_model.p, hm, sizeof(hm), cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_rates.p, c->rates.data(), sizeof(double) * c->K, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_steps.p, c->steps.data(), sizeof(int32_t) * STEP_INTS * n_steps, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_stepoff.p, c->step_off.data(), sizeof(int32_t) * n_steps, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_crec.p, c->crec.data(), sizeof(uint32_t) * 4 * n_steps, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_prec.p, c->prec.data(), sizeof(uint32_t) * 8 * n_steps, cudaMemcpyHostToDevice, s));
+    if (n_cg) CUDA_TRY(c, cudaMemcpyAsync(c->d_cgathers.p, c->clade_gathers.data(), sizeof(int32_t) * 4 * n_cg, cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_slotkind.p, c->slot_kind.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_slotoff.p, c->slot_off.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_slotblen.p, c->slot_blen.data(), sizeof(double) * n_slots, cudaMemcpyHostToDevice, s));
@@ -486,25 +596,22 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     return SR_OK;
 }
 
-template <int M, int NSTAGE, int W, int HOLES = 0, bool ROT = false, bool RA = false, bool TWOPS = false>
 int launch_prune(sr_ctx* c, cudaStream_t s, PruneParams& p, int64_t cols) {
-    using Cfg = PruneCfg<M, W>;
-    const int fixed = NSTAGE * Cfg::STAGE_BYTES + prune_bar_bytes(NSTAGE);
-    int levels = (c->max_smem - fixed) / Cfg::LEVEL_BYTES;
+    const int fixed = P2_NSTAGE * P2_STAGE_BYTES + P2_BAR_BYTES;
+    int levels = (c->max_smem - fixed) / P2_LEVEL_BYTES;
     levels = std::max(0, std::min(levels, c->need_depth));
     const int spill_levels = c->need_depth - levels;
     const int n_items = p.n_tiles * p.K;
     const int grid = std::min(n_items, c->n_sm);
     if (spill_levels > 0)
-        CUDA_TRY(c, c->d_spill.reserve((size_t)grid * spill_levels * Cfg::LEVEL_BYTES));
+        CUDA_TRY(c, c->d_spill.reserve((size_t)grid * spill_levels * P2_LEVEL_BYTES));
     p.smem_levels = levels;
     p.spill_levels = spill_levels;
     p.spill = c->d_spill.as<double>();
-    const int smem = fixed + levels * Cfg::LEVEL_BYTES;
-    auto kern = prune_kernel<M, NSTAGE, W, HOLES, ROT, RA, TWOPS>;
-    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int smem = fixed + levels * P2_LEVEL_BYTES;
+    CUDA_TRY(c, cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prof_begin(c, s, 1, cols);
-    kern<<<grid, prune_threads(W, RA), smem, s>>>(p);
+    prune_kernel<<<grid, P2_THREADS, smem, s>>>(p);
     prof_end(c, s);
     CUDA_TRY(c, cudaGetLastError());
     return SR_OK;
@@ -516,17 +623,26 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     if (n <= 0) return SR_OK;
     int rc = ensure_pstream(c, s);
     if (rc) return rc;
-    const int S = c->warps * c->tile_m * 8;
+    const int S = P2_S;
     const int64_t col_start = (col_begin / 16) * 16;
     const int64_t skip = col_begin - col_start;
     const int64_t tiles = (skip + n + S - 1) / S;
     if (tiles > INT32_MAX / std::max(1, c->K)) return fail(c, SR_ERR_ARG, "too many columns in one launch; lower chunk_cols");
     const int64_t ncp = tiles * S;
+    const int n_cg = (int)c->clade_gathers.size() / 4;
     CUDA_TRY(c, c->d_rootpart.reserve(sizeof(double) * 2 * (size_t)c->K * ncp * NS));
     CUDA_TRY(c, c->d_rootexp.reserve(sizeof(int32_t) * (size_t)c->K * ncp));
+    CUDA_TRY(c, c->d_cidx.reserve(sizeof(uint16_t) * (size_t)std::max(1, n_cg) * ncp));
+    if (n_cg) {
+        // K0b: one table-row index per (clade gather, column). The rows are padded past the launch's last column (the
+        // alignment block's pitch leaves >= 256 bytes of slack, filled with the missing-data code).
+        const unsigned by = (unsigned)std::min<int64_t>((ncp / 2 + 255) / 256, 4096);
+        clade_index_kernel<<<dim3((unsigned)n_cg, by), 256, 0, s>>>(d_states, pitch, col_start, c->d_cgathers.as<int4>(), ncp, c->d_cidx.as<uint16_t>());
+        CUDA_TRY(c, cudaGetLastError());
+    }
     PruneParams p{};
-    p.steps = c->d_steps.as<int4>();
-    p.step_off = c->d_stepoff.as<int32_t>();
+    p.crec = c->d_crec.as<uint4>();
+    p.prec = c->d_prec.as<uint4>();
     p.pstream = c->d_pstream.as<double>();
     p.ctab = c->d_ctab.as<double>();
     p.ctab_rate_stride = c->ctab_rows * CHERRY_ROW_DOUBLES;
@@ -534,48 +650,21 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     p.states = d_states;
     p.pitch = pitch;
     p.col0 = col_start;
+    p.cidx = c->d_cidx.as<uint16_t>();
     p.rootpart = c->d_rootpart.as<double>();
     p.rootexp = c->d_rootexp.as<int32_t>();
     p.ncp = ncp;
     p.n_steps = (int)c->steps.size() / STEP_INTS;
     p.n_tiles = (int)tiles;
     p.K = c->K;
-    p.debug = c->debug;
+    p.k_fastest = c->k_fastest;
+    p.zero = 0;
 #ifdef SR_TIMELINE
     if (c->d_timeline.reserve(sizeof(unsigned) * 16 * SR_TL_STEPS * 8) != cudaSuccess) return fail(c, SR_ERR_OOM, "timeline buffer");
     cudaMemsetAsync(c->d_timeline.p, 0, sizeof(unsigned) * 16 * SR_TL_STEPS * 8, s);
     p.timeline = c->d_timeline.as<unsigned>();
 #endif
-    // kernel variants: tile_m (column tiles per warp), consumer warps, holes in the MMA burst, burst rotation
-    const int hl = c->holes, rot = c->rotate;
-    // template arguments: <tile_m, ring stages, consumer warps, holes, rotation, register re-allocation, two clade gathers>
-    if (c->has_pairs) {
-        // schedules with two clade gathers in a step exist only for the default layout (build_schedule)
-        if (!(c->tile_m == 2 && c->warps == 12 && c->realloc && hl == 2))
-            return fail(c, SR_ERR_UNSUPPORTED, "internal: schedule with clade pairs on a single-gather kernel variant");
-        rc = rot ? launch_prune<2, 4, 12, 2, true, true, true>(c, s, p, n) : launch_prune<2, 4, 12, 2, false, true, true>(c, s, p, n);
-    } else if (c->tile_m == 4 && c->realloc) {
-        rc = rot ? launch_prune<4, 4, 8, 2, true, true>(c, s, p, n) : launch_prune<4, 4, 8, 0, false, true>(c, s, p, n);
-    } else if (c->tile_m == 4) {
-        rc = launch_prune<4, 4, 8>(c, s, p, n);
-    } else if (c->warps == 12) {                       // 12 consumers always run on re-allocated registers
-        if (!rot) rc = launch_prune<2, 4, 12, 2, false, true>(c, s, p, n);
-        else if (hl == 0) rc = launch_prune<2, 4, 12, 0, true, true>(c, s, p, n);
-        else if (hl == 1) rc = launch_prune<2, 4, 12, 1, true, true>(c, s, p, n);
-        else if (hl == 13) rc = launch_prune<2, 4, 12, 13, true, true>(c, s, p, n);
-        else if (hl == 1234) rc = launch_prune<2, 4, 12, 1234, true, true>(c, s, p, n);
-        else rc = launch_prune<2, 4, 12, 2, true, true>(c, s, p, n);
-    } else if (c->warps == 8) {
-        rc = rot ? launch_prune<2, 4, 8, 2, true>(c, s, p, n) : launch_prune<2, 4, 8, 0, false>(c, s, p, n);
-    } else if (c->warps == 15) {
-        rc = rot ? launch_prune<2, 4, 15, 2, true>(c, s, p, n) : launch_prune<2, 4, 15, 0, false>(c, s, p, n);
-    } else {                                           // 11 consumers + producer, 168 registers
-        if (!rot) rc = (hl == 0) ? launch_prune<2, 4, 11, 0, false>(c, s, p, n) : launch_prune<2, 4, 11, 2, false>(c, s, p, n);
-        else if (hl == 0) rc = launch_prune<2, 4, 11, 0, true>(c, s, p, n);
-        else if (hl == 1) rc = launch_prune<2, 4, 11, 1, true>(c, s, p, n);
-        else if (hl == 13) rc = launch_prune<2, 4, 11, 13, true>(c, s, p, n);
-        else rc = launch_prune<2, 4, 11, 2, true>(c, s, p, n);
-    }
+    rc = launch_prune(c, s, p, n);
     if (rc) return rc;
     RootParams r{};
     r.rootpart = p.rootpart;
@@ -585,6 +674,7 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     r.lnl = d_lnl;
     r.joint = d_joint;
     r.compact = d_compact;
+    r.compact_cap = c->compact_cap;
     r.threshold = threshold;
     r.ncp = ncp;
     r.n = n;
@@ -611,7 +701,7 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
 int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch, int n_taxa, int64_t col_begin, int64_t n,
               double* d_lnl, double* d_joint, void* d_compact, double threshold, int64_t out0) {
     if (!c->compress || n < 2) return run_block_plain(c, s, d_states, pitch, col_begin, n, d_lnl, d_joint, d_compact, threshold, out0);
-    if (n > (int64_t)1 << 31) return fail(c, SR_ERR_ARG, "too many columns in one launch; lower chunk_cols");
+    if (n > INT32_MAX) return fail(c, SR_ERR_ARG, "too many columns in one launch; lower chunk_cols");
     const uint8_t* base = d_states + col_begin;
     for (int i = 0; i < 2; ++i) {
         CUDA_TRY(c, c->d_pat_keys[i].reserve(sizeof(uint64_t) * n));
@@ -650,14 +740,14 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
                                                                                    c->d_pat_states.as<uint8_t>(), up);
     CUDA_TRY(c, c->d_pat_lnl.reserve(sizeof(double) * n_uniq));
     if (d_joint) CUDA_TRY(c, c->d_pat_joint.reserve(sizeof(double) * 400 * (size_t)n_uniq));
-    if (d_compact) CUDA_TRY(c, c->d_pat_compact.reserve(sizeof(sr_compact) * (size_t)n_uniq));
+    if (d_compact) CUDA_TRY(c, c->d_pat_compact.reserve((size_t)compact_stride(c->compact_cap) * (size_t)n_uniq));
     int rc = run_block_plain(c, s, c->d_pat_states.as<uint8_t>(), up, 0, n_uniq, c->d_pat_lnl.as<double>(),
                              d_joint ? c->d_pat_joint.as<double>() : nullptr, d_compact ? c->d_pat_compact.p : nullptr, threshold, 0);
     if (rc) return rc;
     scatter_patterns_kernel<<<c->n_sm * 16, 256, 0, s>>>(c->d_pat_map.as<uint32_t>(), n, out0, c->d_pat_lnl.as<double>(),
                                                          d_joint ? c->d_pat_joint.as<double>() : nullptr,
-                                                         d_compact ? c->d_pat_compact.as<uint4>() : nullptr, d_lnl, d_joint,
-                                                         reinterpret_cast<uint4*>(d_compact));
+                                                         d_compact ? c->d_pat_compact.as<uint64_t>() : nullptr, d_lnl, d_joint,
+                                                         reinterpret_cast<uint64_t*>(d_compact), compact_stride(c->compact_cap) / 8);
     CUDA_TRY(c, cudaGetLastError());
     return SR_OK;
 }
@@ -668,8 +758,18 @@ bool is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost;
 }
 
-int check_run_args(sr_ctx* c, int64_t site0, int64_t n, int64_t n_sites, const void* lnl) {
+int compact_cap_for(double threshold) {
+    if (!(threshold > 0.0)) return 400;
+    const double k = std::floor(1.0 / threshold + 1e-9);            // entries >= threshold in a matrix that sums to 1
+    return k >= 400.0 ? 400 : std::max(1, (int)k);
+}
+
+int check_run_args(sr_ctx* c, int64_t site0, int64_t n, int64_t n_sites, const void* lnl, const void* compact = nullptr, double threshold = 0.5) {
     if (!c) return SR_ERR_ARG;
+    if (compact && compact_cap_for(threshold) > c->compact_cap)
+        return fail(c, SR_ERR_ARG, "threshold %g can keep up to %d entries per column but a compact record holds %d: raise option "
+                                   "\"compact_cap\" (records are sr_compact_stride(cap) bytes) or ask for the full joint matrix",
+                    threshold, compact_cap_for(threshold), c->compact_cap);
     if (site0 < 0 || n < 0 || site0 + n > n_sites)
         return fail(c, SR_ERR_ARG, "column range [%lld, %lld) outside the alignment (%lld sites)", (long long)site0,
                     (long long)(site0 + n), (long long)n_sites);
@@ -680,9 +780,10 @@ int check_run_args(sr_ctx* c, int64_t site0, int64_t n, int64_t n_sites, const v
 }  // namespace
 
 // ================================================================================================ ABI
-extern "C" {
+namespace {
 
-int sr_create(sr_ctx** out, int device) {
+
+static int sr_create_impl(sr_ctx** out, int device) {
     if (!out) return fail(nullptr, SR_ERR_ARG, "out is NULL");
     *out = nullptr;
     int n_dev = 0;
@@ -713,25 +814,22 @@ int sr_create(sr_ctx** out, int device) {
         delete c;
         return fail(nullptr, SR_ERR_CUDA, "cannot create CUDA streams");
     }
+    for (int i = 0; i < 3; ++i) {
+        if (cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_sfree[i], cudaEventDisableTiming) != cudaSuccess) {
+            sr_destroy(c);
+            return fail(nullptr, SR_ERR_CUDA, "cannot create CUDA events");
+        }
+    }
     *out = c;
     return SR_OK;
 }
 
-void sr_destroy(sr_ctx* c) {
-    if (!c) return;
-    cudaSetDevice(c->device);
-    cudaDeviceSynchronize();
-    for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    for (int i = 0; i < 3; ++i) if (c->h_bounce[i]) cudaFreeHost(c->h_bounce[i]);
-    if (c->stream) cudaStreamDestroy(c->stream);
-    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
-    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
-    delete c;
-}
 
-const char* sr_last_error(const sr_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
-int sr_set_model(sr_ctx* c, const double* eval, const double* evec, const double* ievc, const double* pi) {
+static int sr_set_model_impl(sr_ctx* c, const double* eval, const double* evec, const double* ievc, const double* pi) {
     if (!c) return SR_ERR_ARG;
     if (!eval || !evec || !ievc || !pi) return fail(c, SR_ERR_ARG, "NULL model array");
     for (int i = 0; i < 20; ++i)
@@ -742,28 +840,35 @@ int sr_set_model(sr_ctx* c, const double* eval, const double* evec, const double
     return SR_OK;
 }
 
-int sr_set_rates(sr_ctx* c, int K, const double* rates) {
+static int check_strict_root(sr_ctx* c);
+
+static int sr_set_rates_impl(sr_ctx* c, int K, const double* rates) {
     if (!c) return SR_ERR_ARG;
     if (K < 1) return fail(c, SR_ERR_ARG, "ERROR: -n (number of rate categories) must be 1 or higher");   // SubRecon.java:209-210
     if (!rates) return fail(c, SR_ERR_ARG, "rates is NULL");
     for (int i = 0; i < K; ++i)
         if (!std::isfinite(rates[i]) || rates[i] < 0.0) return fail(c, SR_ERR_ARG, "rate %d is not a finite non-negative number", i);
     if (K != c->K) c->sched_dirty = true;            // the cherry-table memory cap is per rate class
+    const int old_K = c->K;
     c->K = K;
-    c->rates.assign(rates, rates + K);
     c->has_rates = true;
+    if (int rc = check_strict_root(c)) { c->K = old_K; c->has_rates = !c->rates.empty(); return rc; }
+    c->rates.assign(rates, rates + K);
     c->p_dirty = true;
     return SR_OK;
 }
 
-int sr_set_tree(sr_ctx* c, int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
-                const int32_t* leaf_row, int32_t root) {
-    if (!c) return SR_ERR_ARG;
+// Everything sr_set_tree and the host-only schedule exports accept: CSR arrays that describe ONE rooted tree. Every
+// non-root node must be the child of exactly one parent and be reachable from the root (so no cycle, no node shared
+// by two parents, no orphan), no node has a single child (PAL: "Node with single child enountered"), the root has
+// exactly two children (SubRecon.java:212-213), every tip has an alignment row. `c` only receives the message.
+static int validate_tree(sr_ctx* c, int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                         const int32_t* leaf_row, int32_t root) {
     if (n_nodes < 3 || !child_off || !child_idx || !blen || !leaf_row) return fail(c, SR_ERR_ARG, "bad tree arrays");
     if (root < 0 || root >= n_nodes) return fail(c, SR_ERR_ARG, "root index out of range");
     if (child_off[0] != 0) return fail(c, SR_ERR_ARG, "child_off[0] must be 0");
     for (int v = 0; v < n_nodes; ++v) {
-        const int deg = child_off[v + 1] - child_off[v];
+        const int64_t deg = (int64_t)child_off[v + 1] - child_off[v];
         if (deg < 0) return fail(c, SR_ERR_ARG, "child_off is not monotone at node %d", v);
         if (deg == 1) return fail(c, SR_ERR_ARG, "Node with single child enountered (node %d)", v);   // PAL ReadTree::readNH
         if (deg == 0 && leaf_row[v] < 0) return fail(c, SR_ERR_ARG, "tip node %d has no alignment row (taxon missing from the alignment)", v);
@@ -772,22 +877,61 @@ int sr_set_tree(sr_ctx* c, int32_t n_nodes, const int32_t* child_off, const int3
     }
     const int n_edges = child_off[n_nodes];
     if (n_edges != n_nodes - 1) return fail(c, SR_ERR_ARG, "tree has %d edges for %d nodes", n_edges, n_nodes);
-    for (int e = 0; e < n_edges; ++e)
-        if (child_idx[e] < 0 || child_idx[e] >= n_nodes || child_idx[e] == root) return fail(c, SR_ERR_ARG, "child_idx[%d] invalid", e);
+    std::vector<uint8_t> n_parents(n_nodes, 0);
+    for (int e = 0; e < n_edges; ++e) {
+        const int ch = child_idx[e];
+        if (ch < 0 || ch >= n_nodes || ch == root) return fail(c, SR_ERR_ARG, "child_idx[%d] invalid", e);
+        if (n_parents[ch]++) return fail(c, SR_ERR_ARG, "node %d is listed as a child twice: not a tree", ch);
+    }
     if (child_off[root + 1] - child_off[root] != 2)
         return fail(c, SR_ERR_ARG, "ERROR: Tree root has more than two descendents. Is the tree rooted correctly?");   // SubRecon.java:212-213
+    // n-1 edges and one parent per non-root node: the graph is a tree iff everything hangs off the root
+    std::vector<uint8_t> seen(n_nodes, 0);
+    std::vector<int32_t> st{root};
+    int reached = 0;
+    seen[root] = 1;
+    while (!st.empty()) {
+        const int v = st.back(); st.pop_back();
+        ++reached;
+        for (int e = child_off[v]; e < child_off[v + 1]; ++e)
+            if (!seen[child_idx[e]]) { seen[child_idx[e]] = 1; st.push_back(child_idx[e]); }
+    }
+    if (reached != n_nodes) return fail(c, SR_ERR_ARG, "tree is not connected: %d of %d nodes reachable from the root (cycle?)", reached, n_nodes);
+    return SR_OK;
+}
+
+// The reference cannot handle a tip as a root child when K > 1: every column throws inside getLnSumComponents
+// (utils/Utils.java:56-70) and is skipped (SubRecon.java:127-135). With option "strict_root" that input is
+// rejected up front, as SURVEY §8(b) asks; without it the native path returns the well-defined limit.
+static int check_strict_root(sr_ctx* c) {
+    if (!c->strict_root || !c->has_tree || !c->has_rates || c->K <= 1) return SR_OK;
+    for (int e = c->child_off[c->root]; e < c->child_off[c->root + 1]; ++e) {
+        const int v = c->child_idx[e];
+        if (c->child_off[v] == c->child_off[v + 1])
+            return fail(c, SR_ERR_UNSUPPORTED, "a child of the root is a tip (node %d) and K = %d > 1: the reference fails on every column "
+                                               "of such a tree (utils/Utils.java:56-70); re-root the tree or use one rate class", v, c->K);
+    }
+    return SR_OK;
+}
+
+static int sr_set_tree_impl(sr_ctx* c, int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                const int32_t* leaf_row, int32_t root) {
+    if (!c) return SR_ERR_ARG;
+    int rc = validate_tree(c, n_nodes, child_off, child_idx, blen, leaf_row, root);
+    if (rc) return rc;
     c->n_nodes = n_nodes;
     c->root = root;
     c->child_off.assign(child_off, child_off + n_nodes + 1);
-    c->child_idx.assign(child_idx, child_idx + n_edges);
+    c->child_idx.assign(child_idx, child_idx + child_off[n_nodes]);
     c->blen.assign(blen, blen + n_nodes);
     c->leaf_row.assign(leaf_row, leaf_row + n_nodes);
     c->has_tree = true;
     c->sched_dirty = true;
+    if ((rc = check_strict_root(c))) { c->has_tree = false; return rc; }
     return build_schedule(c);
 }
 
-int sr_set_alignment(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* states, int64_t pitch) {
+static int sr_set_alignment_impl(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* states, int64_t pitch) {
     if (!c) return SR_ERR_ARG;
     if (n_taxa < 1 || n_sites < 0 || !states || pitch < n_sites) return fail(c, SR_ERR_ARG, "bad alignment arguments");
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -808,11 +952,11 @@ int sr_set_alignment(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* 
     return SR_OK;
 }
 
-int sr_run_device(sr_ctx* c, int64_t site0, int64_t n, double* d_lnl, double* d_joint, sr_compact* d_compact,
+static int sr_run_device_impl(sr_ctx* c, int64_t site0, int64_t n, double* d_lnl, double* d_joint, sr_compact* d_compact,
                   double threshold, void* stream) {
     if (!c) return SR_ERR_ARG;
     if (!c->has_aln) return fail(c, SR_ERR_STATE, "alignment not set");
-    int rc = check_run_args(c, site0, n, c->aln_sites, d_lnl ? (void*)d_lnl : (void*)d_joint);
+    int rc = check_run_args(c, site0, n, c->aln_sites, d_lnl ? (void*)d_lnl : (void*)d_joint, d_compact, threshold);
     if (rc) return rc;
     if (c->has_tree && c->max_leaf_row >= c->aln_taxa) return fail(c, SR_ERR_ARG, "tree refers to alignment row %d but the alignment has %d taxa", c->max_leaf_row, c->aln_taxa);
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -829,7 +973,7 @@ int sr_run_device(sr_ctx* c, int64_t site0, int64_t n, double* d_lnl, double* d_
 // Results back to the caller. Page-locked destinations (sr_host_alloc) are DMA'd asynchronously on the D2H stream, which
 // already waits for `done`. Pageable destinations are copied synchronously after the host itself has waited for `done`:
 // asynchronous copies involving pageable memory are staged by the driver and are not something to order by stream events.
-static int d2h(sr_ctx* c, cudaStream_t s, cudaEvent_t done, bool pinned, void* dst, const void* src, size_t bytes) {
+int d2h(sr_ctx* c, cudaStream_t s, cudaEvent_t done, bool pinned, void* dst, const void* src, size_t bytes) {
     if (pinned) {
         CUDA_TRY(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
     } else {
@@ -839,17 +983,18 @@ static int d2h(sr_ctx* c, cudaStream_t s, cudaEvent_t done, bool pinned, void* d
     return SR_OK;
 }
 
-int sr_run(sr_ctx* c, int64_t site0, int64_t n, double* lnl, double* joint, sr_compact* compact, double threshold) {
+static int sr_run_impl(sr_ctx* c, int64_t site0, int64_t n, double* lnl, double* joint, sr_compact* compact, double threshold) {
     if (!c) return SR_ERR_ARG;
     if (!c->has_aln) return fail(c, SR_ERR_STATE, "alignment not set");
-    int rc = check_run_args(c, site0, n, c->aln_sites, lnl);
+    int rc = check_run_args(c, site0, n, c->aln_sites, lnl, compact, threshold);
+    const size_t cstride = (size_t)compact_stride(c->compact_cap);
     if (rc) return rc;
     if (c->has_tree && c->max_leaf_row >= c->aln_taxa) return fail(c, SR_ERR_ARG, "tree refers to alignment row %d but the alignment has %d taxa", c->max_leaf_row, c->aln_taxa);
     CUDA_TRY(c, cudaSetDevice(c->device));
     // chunked: compute chunk i on `stream` while chunk i-1 drains to the host on `s_d2h`
     const int64_t chunk = std::min<int64_t>(c->chunk_cols, std::max<int64_t>(n, 1));
-    cudaEvent_t done_ev[2], free_ev[2];
-    for (int i = 0; i < 2; ++i) { CUDA_TRY(c, cudaEventCreateWithFlags(&done_ev[i], cudaEventDisableTiming)); CUDA_TRY(c, cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming)); }
+    cudaEvent_t* done_ev = c->ev_done;
+    cudaEvent_t* free_ev = c->ev_free;
     const bool pin_lnl = is_pinned(lnl), pin_joint = joint && is_pinned(joint), pin_compact = compact && is_pinned(compact);
     int ci = 0;
     rc = SR_OK;
@@ -858,21 +1003,20 @@ int sr_run(sr_ctx* c, int64_t site0, int64_t n, double* lnl, double* joint, sr_c
         const int64_t m = std::min(n - done, chunk);
         if ((rc = (c->d_chunk_lnl[b].reserve(sizeof(double) * m) == cudaSuccess ? SR_OK : fail(c, SR_ERR_OOM, "device OOM (lnl chunk)")))) break;
         if (joint && c->d_chunk_joint[b].reserve(sizeof(double) * 400 * m) != cudaSuccess) { rc = fail(c, SR_ERR_OOM, "device OOM (joint chunk)"); break; }
-        if (compact && c->d_chunk_compact[b].reserve(sizeof(sr_compact) * m) != cudaSuccess) { rc = fail(c, SR_ERR_OOM, "device OOM (compact chunk)"); break; }
-        if (ci >= 2) cudaStreamWaitEvent(c->stream, free_ev[b], 0);      // buffer b drained?
+        if (compact && c->d_chunk_compact[b].reserve(cstride * m) != cudaSuccess) { rc = fail(c, SR_ERR_OOM, "device OOM (compact chunk)"); break; }
+        if (ci >= 2) CUDA_STEP(c, rc, cudaStreamWaitEvent(c->stream, free_ev[b], 0));      // buffer b drained?
         rc = run_block(c, c->stream, c->d_states.as<uint8_t>(), c->aln_pitch, c->aln_taxa, site0 + done, m, c->d_chunk_lnl[b].as<double>(),
                        joint ? c->d_chunk_joint[b].as<double>() : nullptr, compact ? c->d_chunk_compact[b].p : nullptr, threshold, 0);
         if (rc) break;
-        cudaEventRecord(done_ev[b], c->stream);
-        cudaStreamWaitEvent(c->s_d2h, done_ev[b], 0);
+        CUDA_STEP(c, rc, cudaEventRecord(done_ev[b], c->stream));
+        CUDA_STEP(c, rc, cudaStreamWaitEvent(c->s_d2h, done_ev[b], 0));
         if ((rc = d2h(c, c->s_d2h, done_ev[b], pin_lnl, lnl + done, c->d_chunk_lnl[b].p, sizeof(double) * m))) break;
         if (joint && (rc = d2h(c, c->s_d2h, done_ev[b], pin_joint, joint + done * 400, c->d_chunk_joint[b].p, sizeof(double) * 400 * m))) break;
-        if (compact && (rc = d2h(c, c->s_d2h, done_ev[b], pin_compact, compact + done, c->d_chunk_compact[b].p, sizeof(sr_compact) * m))) break;
-        cudaEventRecord(free_ev[b], c->s_d2h);
+        if (compact && (rc = d2h(c, c->s_d2h, done_ev[b], pin_compact, reinterpret_cast<char*>(compact) + cstride * done, c->d_chunk_compact[b].p, cstride * m))) break;
+        CUDA_STEP(c, rc, cudaEventRecord(free_ev[b], c->s_d2h));
         done += m;
     }
     cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_d2h);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(done_ev[i]); cudaEventDestroy(free_ev[i]); }
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         cudaGetLastError();
@@ -881,11 +1025,12 @@ int sr_run(sr_ctx* c, int64_t site0, int64_t n, double* lnl, double* joint, sr_c
     return SR_OK;
 }
 
-int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* states, int64_t pitch, int64_t site0,
+static int sr_run_streamed_impl(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* states, int64_t pitch, int64_t site0,
                     int64_t n, double* lnl, double* joint, sr_compact* compact, double threshold) {
     if (!c) return SR_ERR_ARG;
     if (n_taxa < 1 || !states || pitch < n_sites) return fail(c, SR_ERR_ARG, "bad alignment arguments");
-    int rc = check_run_args(c, site0, n, n_sites, lnl);
+    int rc = check_run_args(c, site0, n, n_sites, lnl, compact, threshold);
+    const size_t cstride = (size_t)compact_stride(c->compact_cap);
     if (rc) return rc;
     if (c->has_tree && c->max_leaf_row >= n_taxa) return fail(c, SR_ERR_ARG, "tree refers to alignment row %d but the alignment has %d taxa", c->max_leaf_row, n_taxa);
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -899,7 +1044,7 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
     // (tiles x K work items must be a multiple of the SM count, or the last wave of every chunk runs part empty).
     int64_t chunk;
     {
-        const int64_t S = (int64_t)c->warps * c->tile_m * 8;
+        const int64_t S = P2_S;
         int64_t g = c->n_sm, b = std::max(1, c->K);
         while (b) { const int64_t t = g % b; g = b; b = t; }
         const int64_t unit = (c->n_sm / g) * S;                       // columns per whole wave set
@@ -908,20 +1053,17 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
         chunk = std::max<int64_t>(256, (chunk + 15) / 16 * 16);
     }
     const int64_t cpitch = (chunk + 255) / 256 * 256 + 256;
-    cudaEvent_t up_ev[NB], done_ev[NB], free_ev[NB], sfree_ev[NB];
-    for (int i = 0; i < NB; ++i) {
-        CUDA_TRY(c, cudaEventCreateWithFlags(&up_ev[i], cudaEventDisableTiming));
-        CUDA_TRY(c, cudaEventCreateWithFlags(&done_ev[i], cudaEventDisableTiming));
-        CUDA_TRY(c, cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming));
-        CUDA_TRY(c, cudaEventCreateWithFlags(&sfree_ev[i], cudaEventDisableTiming));
-    }
+    cudaEvent_t* up_ev = c->ev_up;
+    cudaEvent_t* done_ev = c->ev_done;
+    cudaEvent_t* free_ev = c->ev_free;
+    cudaEvent_t* sfree_ev = c->ev_sfree;
     const bool src_pinned = is_pinned(states);
     const bool pin_lnl = is_pinned(lnl), pin_joint = joint && is_pinned(joint), pin_compact = compact && is_pinned(compact);
     // Chunk sizes: full chunks in the middle, a ramp of short ones at both ends. The pipeline's exposed time is the
     // upload of the first chunk plus the download of the last one (3200 B per column of joint output).
     std::vector<int64_t> sizes;
     {
-        const int64_t S = (int64_t)c->warps * c->tile_m * 8;
+        const int64_t S = P2_S;
         int64_t g = c->n_sm, b = std::max(1, c->K);
         while (b) { const int64_t t = g % b; g = b; b = t; }
         const int64_t unit = (c->n_sm / g) * S;
@@ -950,7 +1092,7 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
         if (c->d_chunk_states[b].reserve((size_t)cpitch * n_taxa + 512) != cudaSuccess ||
             c->d_chunk_lnl[b].reserve(sizeof(double) * mmax) != cudaSuccess ||
             (joint && c->d_chunk_joint[b].reserve(sizeof(double) * 400 * mmax) != cudaSuccess) ||
-            (compact && c->d_chunk_compact[b].reserve(sizeof(sr_compact) * mmax) != cudaSuccess)) {
+            (compact && c->d_chunk_compact[b].reserve(cstride * mmax) != cudaSuccess)) {
             cudaGetLastError();
             rc = fail(c, SR_ERR_OOM, "device OOM (pipeline chunk buffers)");
         }
@@ -970,7 +1112,7 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
     for (size_t ci = 0; ci < sizes.size() && rc == SR_OK; ++ci) {
         const int b = (int)(ci % NB);
         const int64_t m = sizes[ci];
-        if (ci >= NB) cudaStreamWaitEvent(c->s_h2d, sfree_ev[b], 0);    // kernels of chunk ci-NB have consumed states buffer b
+        if (ci >= NB) CUDA_STEP(c, rc, cudaStreamWaitEvent(c->s_h2d, sfree_ev[b], 0));    // kernels of chunk ci-NB have consumed states buffer b
         const uint8_t* src = states + site0 + done;
         int64_t src_pitch = pitch;
         if (!src_pinned) {
@@ -979,7 +1121,7 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
             // page-locked bounce buffer on the host thread instead; the DMA then runs from pinned memory like any other.
             const size_t need = (size_t)mmax * n_taxa;                   // sized for a full chunk once, not per ramp step
             if (c->h_bounce_cap[b] < need) {
-                if (c->h_bounce[b]) { cudaEventSynchronize(up_ev[b]); cudaFreeHost(c->h_bounce[b]); c->h_bounce[b] = nullptr; c->h_bounce_cap[b] = 0; }
+                if (c->h_bounce[b]) { if (ci >= NB) cudaEventSynchronize(up_ev[b]); cudaFreeHost(c->h_bounce[b]); c->h_bounce[b] = nullptr; c->h_bounce_cap[b] = 0; }
                 if (cudaMallocHost(&c->h_bounce[b], need) != cudaSuccess) { cudaGetLastError(); rc = fail(c, SR_ERR_OOM, "cannot allocate the pinned staging buffer"); break; }
                 c->h_bounce_cap[b] = need;
             } else if (ci >= NB) {
@@ -995,23 +1137,24 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
         if (e != cudaSuccess) { rc = fail(c, SR_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
         if (c->input_chars) encode_chars_kernel<<<c->n_sm * 4, 256, 0, c->s_h2d>>>(c->d_chunk_states[b].as<uint4>(), ((size_t)cpitch * n_taxa + 512) / 16);
         else sanitize_kernel<<<c->n_sm * 4, 256, 0, c->s_h2d>>>(c->d_chunk_states[b].as<uint4>(), ((size_t)cpitch * n_taxa + 512) / 16);
-        cudaEventRecord(up_ev[b], c->s_h2d);
+        CUDA_STEP(c, rc, cudaGetLastError());
+        CUDA_STEP(c, rc, cudaEventRecord(up_ev[b], c->s_h2d));
         SR_PIPE_EV(h1, c->s_h2d);
-        cudaStreamWaitEvent(c->stream, up_ev[b], 0);
-        if (ci >= NB) cudaStreamWaitEvent(c->stream, free_ev[b], 0);    // output buffers b drained
+        CUDA_STEP(c, rc, cudaStreamWaitEvent(c->stream, up_ev[b], 0));
+        if (ci >= NB) CUDA_STEP(c, rc, cudaStreamWaitEvent(c->stream, free_ev[b], 0));    // output buffers b drained
         SR_PIPE_EV(k0, c->stream);
         rc = run_block(c, c->stream, c->d_chunk_states[b].as<uint8_t>(), cpitch, n_taxa, 0, m, c->d_chunk_lnl[b].as<double>(),
                        joint ? c->d_chunk_joint[b].as<double>() : nullptr, compact ? c->d_chunk_compact[b].p : nullptr, threshold, 0);
         if (rc) break;
-        cudaEventRecord(done_ev[b], c->stream);
-        cudaEventRecord(sfree_ev[b], c->stream);
+        CUDA_STEP(c, rc, cudaEventRecord(done_ev[b], c->stream));
+        CUDA_STEP(c, rc, cudaEventRecord(sfree_ev[b], c->stream));
         SR_PIPE_EV(k1, c->stream);
-        cudaStreamWaitEvent(c->s_d2h, done_ev[b], 0);
+        CUDA_STEP(c, rc, cudaStreamWaitEvent(c->s_d2h, done_ev[b], 0));
         SR_PIPE_EV(d0, c->s_d2h);
         if ((rc = d2h(c, c->s_d2h, done_ev[b], pin_lnl, lnl + done, c->d_chunk_lnl[b].p, sizeof(double) * m))) break;
         if (joint && (rc = d2h(c, c->s_d2h, done_ev[b], pin_joint, joint + done * 400, c->d_chunk_joint[b].p, sizeof(double) * 400 * m))) break;
-        if (compact && (rc = d2h(c, c->s_d2h, done_ev[b], pin_compact, compact + done, c->d_chunk_compact[b].p, sizeof(sr_compact) * m))) break;
-        cudaEventRecord(free_ev[b], c->s_d2h);
+        if (compact && (rc = d2h(c, c->s_d2h, done_ev[b], pin_compact, reinterpret_cast<char*>(compact) + cstride * done, c->d_chunk_compact[b].p, cstride * m))) break;
+        CUDA_STEP(c, rc, cudaEventRecord(free_ev[b], c->s_d2h));
         SR_PIPE_EV(d1, c->s_d2h);
         tl_set_m(ci, m);
         done += m;
@@ -1028,7 +1171,6 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
     }
     for (auto& e : tl) { cudaEventDestroy(e.h0); cudaEventDestroy(e.h1); cudaEventDestroy(e.k0); cudaEventDestroy(e.k1); cudaEventDestroy(e.d0); cudaEventDestroy(e.d1); }
 #endif
-    for (int i = 0; i < NB; ++i) { cudaEventDestroy(up_ev[i]); cudaEventDestroy(done_ev[i]); cudaEventDestroy(free_ev[i]); cudaEventDestroy(sfree_ev[i]); }
     if (rc) return rc;
     if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
         cudaGetLastError();
@@ -1037,43 +1179,23 @@ int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* s
     return SR_OK;
 }
 
-void* sr_host_alloc(size_t bytes) {
-    void* p = nullptr;
-    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return p;
-}
 
-void sr_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
+static int sr_set_option_impl(sr_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return SR_ERR_ARG;
     const std::string k(name);
-    if (k == "tile_m") {
-        if (value != 2 && value != 4) return fail(c, SR_ERR_ARG, "tile_m must be 2 or 4");
-        c->tile_m = (int)value;
-        c->warps = (value == 4) ? 8 : 12;
-        c->realloc = (value == 2);
-        c->sched_dirty = true;
-    } else if (k == "warps") {
-        // register files are allocated in 4-warp granules: with the producer warp, 11 and 15 consumers are "free"
-        if (value != 8 && value != 11 && value != 12 && value != 15) return fail(c, SR_ERR_ARG, "warps must be 8, 11, 12 or 15");
-        if (c->tile_m == 4 && value != 8) return fail(c, SR_ERR_ARG, "tile_m 4 supports 8 warps only");
-        c->warps = (int)value;
-        c->realloc = (value == 12);                  // 12 consumers only exist on re-allocated registers
-        c->sched_dirty = true;
-    } else if (k == "realloc") {
-        // dedicated producer warp living on re-allocated registers (setmaxnreg): 12 consumers x tile_m 2, or 8 x tile_m 4
-        c->realloc = value != 0;
-        if (c->realloc) c->warps = (c->tile_m == 4) ? 8 : 12;
-        else if (c->tile_m == 2 && c->warps == 12) c->warps = 11;
-        c->sched_dirty = true;
+    if (k == "debug") {
+        c->debug = (int)value;
+    } else if (k == "compact_cap") {
+        if (value < 1 || value > 400) return fail(c, SR_ERR_ARG, "compact_cap must be in 1..400");
+        c->compact_cap = (int)value;
+    } else if (k == "k_fastest") {
+        c->k_fastest = value != 0;
+    } else if (k == "strict_root") {
+        c->strict_root = value != 0;
     } else if (k == "chunk_cols") {
         if (value < 256) return fail(c, SR_ERR_ARG, "chunk_cols must be >= 256");
         c->chunk_cols = (value + 255) / 256 * 256;
-    } else if (k == "holes") {
-        if (value < 0 || value > 1234) return fail(c, SR_ERR_ARG, "holes must be 0, 1, 2 or the digits of the k-steps (1..4) to pause before");
-        c->holes = (int)value;
-        c->sched_dirty = true;
     } else if (k == "compress_patterns") {
         c->compress = value != 0;
         c->last_unique = c->last_total = 0;
@@ -1092,10 +1214,6 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
         c->sched_dirty = true;
     } else if (k == "input_chars") {
         c->input_chars = value != 0;                  // applies to the next sr_set_alignment / sr_run_streamed
-    } else if (k == "debug") {
-        c->debug = (int)value;
-    } else if (k == "rotate") {
-        c->rotate = value != 0;
     } else if (k == "stream_chunk_cols") {
         if (value < 256) return fail(c, SR_ERR_ARG, "stream_chunk_cols must be >= 256");
         c->stream_chunk_cols = (value + 255) / 256 * 256;
@@ -1104,7 +1222,10 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     } else if (k == "profile") {
         c->profile = value != 0;
     } else if (k == "rescale_every") {
-        if (value < 1 || value > 20) return fail(c, SR_ERR_ARG, "rescale_every must be in 1..20");
+        // Upper bound 12: between two rescalings a partial can collect about twice the period (a popped sibling brings
+        // its own un-rescaled edges, a clade gather counts two or three), each edge costing up to ~1e-13 at the 1e-9
+        // branch-length clamp; 12 still passes tests/test_gpu_parity.py::test_adversarial_underflow, 16 does not.
+        if (value < 1 || value > 12) return fail(c, SR_ERR_ARG, "rescale_every must be in 1..12");
         c->rescale_every = (int)value;
         c->sched_dirty = true;
     } else {
@@ -1113,7 +1234,7 @@ int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
     return SR_OK;
 }
 
-int sr_get_profile(sr_ctx* c, sr_profile* out) {
+static int sr_get_profile_impl(sr_ctx* c, sr_profile* out) {
     if (!c || !out) return SR_ERR_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaDeviceSynchronize());
@@ -1135,7 +1256,7 @@ int sr_get_profile(sr_ctx* c, sr_profile* out) {
     return SR_OK;
 }
 
-int sr_profile_reset(sr_ctx* c) {
+static int sr_profile_reset_impl(sr_ctx* c) {
     if (!c) return SR_ERR_ARG;
     sr_profile tmp;
     int rc = sr_get_profile(c, &tmp);
@@ -1144,7 +1265,7 @@ int sr_profile_reset(sr_ctx* c) {
     return rc;
 }
 
-int sr_schedule_info(sr_ctx* c, int64_t* n_steps, int32_t* stack_depth, double* flops) {
+static int sr_schedule_info_impl(sr_ctx* c, int64_t* n_steps, int32_t* stack_depth, double* flops) {
     if (!c) return SR_ERR_ARG;
     if (!c->has_tree) return fail(c, SR_ERR_STATE, "tree not set");
     if (c->sched_dirty) { int rc = build_schedule(c); if (rc) return rc; }
@@ -1154,22 +1275,28 @@ int sr_schedule_info(sr_ctx* c, int64_t* n_steps, int32_t* stack_depth, double* 
     return SR_OK;
 }
 
-int sr_schedule_dump(int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
-                     const int32_t* leaf_row, int32_t root, int32_t rescale_every, int32_t cherry_tables, int64_t cap_steps,
-                     int32_t* steps, int32_t* node_slot, int64_t* n_steps, int32_t* stack_depth) {
-    // host-only: builds the schedule exactly as sr_set_tree does, without touching a GPU
-    if (n_nodes < 3 || !child_off || !child_idx || !blen || !leaf_row || !n_steps) return SR_ERR_ARG;
-    if (root < 0 || root >= n_nodes || child_off[root + 1] - child_off[root] != 2) return SR_ERR_ARG;
-    sr_ctx tmp;
+static int host_schedule(sr_ctx& tmp, int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                         const int32_t* leaf_row, int32_t root, int32_t rescale_every, int32_t cherry_tables) {
+    int rc = validate_tree(&tmp, n_nodes, child_off, child_idx, blen, leaf_row, root);
+    if (rc) return rc;
     tmp.n_nodes = n_nodes;
     tmp.root = root;
     tmp.child_off.assign(child_off, child_off + n_nodes + 1);
     tmp.child_idx.assign(child_idx, child_idx + child_off[n_nodes]);
     tmp.blen.assign(blen, blen + n_nodes);
     tmp.leaf_row.assign(leaf_row, leaf_row + n_nodes);
-    tmp.rescale_every = rescale_every > 0 ? rescale_every : 8;
+    tmp.rescale_every = (rescale_every > 0 && rescale_every <= 12) ? rescale_every : 8;
     tmp.cherry_tables = cherry_tables != 0;
-    int rc = build_schedule(&tmp);
+    return build_schedule(&tmp);
+}
+
+static int sr_schedule_dump_impl(int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                     const int32_t* leaf_row, int32_t root, int32_t rescale_every, int32_t cherry_tables, int64_t cap_steps,
+                     int32_t* steps, int32_t* node_slot, int64_t* n_steps, int32_t* stack_depth) {
+    // host-only: builds the schedule exactly as sr_set_tree does, without touching a GPU
+    if (!n_steps) return SR_ERR_ARG;
+    sr_ctx tmp;
+    int rc = host_schedule(tmp, n_nodes, child_off, child_idx, blen, leaf_row, root, rescale_every, cherry_tables);
     if (rc) return rc;
     *n_steps = (int64_t)tmp.steps.size() / STEP_INTS;
     if (stack_depth) *stack_depth = tmp.need_depth;
@@ -1181,7 +1308,24 @@ int sr_schedule_dump(int32_t n_nodes, const int32_t* child_off, const int32_t* c
     return SR_OK;
 }
 
-int sr_measure_fp64_peak(sr_ctx* c, double ms_target, double* tflops) {
+static int sr_schedule_records_impl(int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                     const int32_t* leaf_row, int32_t root, int32_t rescale_every, int32_t cherry_tables, int64_t cap_steps,
+                     uint32_t* crec, uint32_t* prec, int32_t* clade_gathers, int64_t* n_steps, int64_t* n_clade_gathers) {
+    // host-only: the two record streams prune_kernel reads (prune.cuh), for the CPU test that interprets them
+    if (!n_steps || !n_clade_gathers || !crec || !prec || !clade_gathers) return SR_ERR_ARG;
+    sr_ctx tmp;
+    int rc = host_schedule(tmp, n_nodes, child_off, child_idx, blen, leaf_row, root, rescale_every, cherry_tables);
+    if (rc) return rc;
+    *n_steps = (int64_t)tmp.steps.size() / STEP_INTS;
+    *n_clade_gathers = (int64_t)tmp.clade_gathers.size() / 4;
+    if (*n_steps > cap_steps || *n_clade_gathers > 3 * cap_steps) return SR_ERR_ARG;
+    memcpy(crec, tmp.crec.data(), sizeof(uint32_t) * tmp.crec.size());
+    memcpy(prec, tmp.prec.data(), sizeof(uint32_t) * tmp.prec.size());
+    memcpy(clade_gathers, tmp.clade_gathers.data(), sizeof(int32_t) * tmp.clade_gathers.size());
+    return SR_OK;
+}
+
+static int sr_measure_fp64_peak_impl(sr_ctx* c, double ms_target, double* tflops) {
     if (!c || !tflops) return SR_ERR_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, c->d_peak.reserve(64));
@@ -1207,7 +1351,7 @@ int sr_measure_fp64_peak(sr_ctx* c, double ms_target, double* tflops) {
     return SR_OK;
 }
 
-int sr_debug_pmatrix(sr_ctx* c, int32_t node, int32_t k, double* out) {
+static int sr_debug_pmatrix_impl(sr_ctx* c, int32_t node, int32_t k, double* out) {
     if (!c || !out) return SR_ERR_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc = ensure_pstream(c, c->stream);
@@ -1235,12 +1379,12 @@ int sr_debug_pmatrix(sr_ctx* c, int32_t node, int32_t k, double* out) {
         }
     } else {
         for (int s = 0; s < 20; ++s)
-            for (int i = 0; i < 20; ++i) out[i * 20 + s] = buf[s * 20 + i];
+            for (int i = 0; i < 20; ++i) out[i * 20 + s] = buf[s * TAB_ROW_DOUBLES + (i / 5) * 6 + i % 5];
     }
     return SR_OK;
 }
 
-int sr_debug_cherry_table(sr_ctx* c, int32_t node, int32_t k, double* out, int64_t cap_doubles, int32_t* n_rows) {
+static int sr_debug_cherry_table_impl(sr_ctx* c, int32_t node, int32_t k, double* out, int64_t cap_doubles, int32_t* n_rows) {
     if (!c || !out) return SR_ERR_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc = ensure_pstream(c, c->stream);
@@ -1263,12 +1407,252 @@ int sr_debug_cherry_table(sr_ctx* c, int32_t node, int32_t k, double* out, int64
 
 #ifdef SR_TIMELINE
 // tools/timeline.py only (not part of the ABI): clock stamps of the last prune launch, [16 warps][SR_TL_STEPS][8]
-int sr_debug_timeline(sr_ctx* c, unsigned* out, int64_t n_words) {
+static int sr_debug_timeline_impl(sr_ctx* c, unsigned* out, int64_t n_words) {
     if (!c || !out || !c->d_timeline.p) return SR_ERR_ARG;
     CUDA_TRY(c, cudaDeviceSynchronize());
     CUDA_TRY(c, cudaMemcpy(out, c->d_timeline.p, sizeof(unsigned) * std::min<int64_t>(n_words, 16 * SR_TL_STEPS * 8), cudaMemcpyDeviceToHost));
     return SR_OK;
 }
 #endif
+
+
+
+// ================================================================================================ one process, N GPUs
+}  // namespace
+
+struct sr_multi {
+    std::vector<sr_ctx*> ctx;
+    std::string err;
+};
+
+namespace {
+
+thread_local std::string g_multi_create_error;
+
+int mfail(sr_multi* m, int code, const char* fmt, ...) noexcept {
+    char buf[640];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    try {
+        if (m) m->err = buf; else g_multi_create_error = buf;
+    } catch (...) {
+    }
+    return code;
+}
+
+template <typename F>
+int mguarded(sr_multi* m, F&& f) noexcept {
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        return mfail(m, SR_ERR_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return mfail(m, SR_ERR_ARG, "internal error: %s", e.what());
+    } catch (...) {
+        return mfail(m, SR_ERR_ARG, "internal error");
+    }
+}
+
+// run f(ctx, g) for every context on its own host thread; the first failure (lowest device) is reported
+template <typename F>
+int multi_each(sr_multi* m, F&& f) {
+    const int G = (int)m->ctx.size();
+    std::vector<int> rc(G, SR_OK);
+    if (G == 1) {
+        rc[0] = f(m->ctx[0], 0);
+    } else {
+        std::vector<std::thread> th;
+        th.reserve(G);
+        for (int g = 0; g < G; ++g)
+            th.emplace_back([&, g] { rc[g] = guarded(m->ctx[g], [&] { return f(m->ctx[g], g); }); });
+        for (auto& t : th) t.join();
+    }
+    for (int g = 0; g < G; ++g)
+        if (rc[g]) return mfail(m, rc[g], "device %d: %s", m->ctx[g]->device, m->ctx[g]->err.c_str());
+    return SR_OK;
+}
+
+int sr_multi_create_impl(sr_multi** out, int n_dev, const int* dev_ids) {
+    if (!out) return mfail(nullptr, SR_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible == 0) {
+        cudaGetLastError();
+        return mfail(nullptr, SR_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (n_dev <= 0) { n_dev = visible; dev_ids = nullptr; }
+    sr_multi* m = new sr_multi();
+    for (int g = 0; g < n_dev; ++g) {
+        sr_ctx* c = nullptr;
+        const int rc = sr_create(&c, dev_ids ? dev_ids[g] : g);
+        if (rc) {
+            mfail(nullptr, rc, "%s", sr_last_error(nullptr));
+            for (sr_ctx* x : m->ctx) sr_destroy(x);
+            delete m;
+            return rc;
+        }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return SR_OK;
+}
+
+int sr_multi_run_streamed_impl(sr_multi* m, int32_t n_taxa, int64_t n_sites, const uint8_t* states, int64_t pitch, int64_t site0,
+                               int64_t n, double* lnl, double* joint, sr_compact* compact, double threshold) {
+    if (!m) return SR_ERR_ARG;
+    if (site0 < 0 || n < 0 || site0 + n > n_sites) return mfail(m, SR_ERR_ARG, "column range outside the alignment");
+    const int G = (int)m->ctx.size();
+    // contiguous blocks of ceil(n / G) columns; whole 16-column groups so that every block starts aligned
+    int64_t per = (n + G - 1) / G;
+    per = (per + 15) / 16 * 16;
+    return multi_each(m, [&](sr_ctx* c, int g) {
+        const int64_t b0 = std::min<int64_t>(n, (int64_t)g * per), b1 = std::min<int64_t>(n, b0 + per);
+        if (b1 <= b0) return (int)SR_OK;
+        const size_t cstride = (size_t)compact_stride(c->compact_cap);
+        return sr_run_streamed_impl(c, n_taxa, n_sites, states, pitch, site0 + b0, b1 - b0, lnl ? lnl + b0 : nullptr,
+                                    joint ? joint + b0 * 400 : nullptr,
+                                    compact ? reinterpret_cast<sr_compact*>(reinterpret_cast<char*>(compact) + cstride * b0) : nullptr, threshold);
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+int sr_compact_cap_for(double threshold) { return compact_cap_for(threshold); }
+size_t sr_compact_stride(int cap) { return (cap < 1 || cap > 400) ? 0 : (size_t)compact_stride(cap); }
+
+int sr_multi_create(sr_multi** out, int n_dev, const int* dev_ids) {
+    return mguarded(nullptr, [&] { return sr_multi_create_impl(out, n_dev, dev_ids); });
+}
+void sr_multi_destroy(sr_multi* m) {
+    if (!m) return;
+    for (sr_ctx* c : m->ctx) sr_destroy(c);
+    delete m;
+}
+const char* sr_multi_last_error(const sr_multi* m) { return m ? m->err.c_str() : g_multi_create_error.c_str(); }
+int sr_multi_count(const sr_multi* m) { return m ? (int)m->ctx.size() : 0; }
+sr_ctx* sr_multi_ctx(sr_multi* m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr; }
+int sr_multi_set_model(sr_multi* m, const double* eval, const double* evec, const double* ievc, const double* pi) {
+    if (!m) return SR_ERR_ARG;
+    return mguarded(m, [&] { return multi_each(m, [&](sr_ctx* c, int) { return sr_set_model_impl(c, eval, evec, ievc, pi); }); });
+}
+int sr_multi_set_rates(sr_multi* m, int K, const double* rates) {
+    if (!m) return SR_ERR_ARG;
+    return mguarded(m, [&] { return multi_each(m, [&](sr_ctx* c, int) { return sr_set_rates_impl(c, K, rates); }); });
+}
+int sr_multi_set_tree(sr_multi* m, int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                      const int32_t* leaf_row, int32_t root) {
+    if (!m) return SR_ERR_ARG;
+    return mguarded(m, [&] { return multi_each(m, [&](sr_ctx* c, int) { return sr_set_tree_impl(c, n_nodes, child_off, child_idx, blen, leaf_row, root); }); });
+}
+int sr_multi_set_option(sr_multi* m, const char* name, int64_t value) {
+    if (!m) return SR_ERR_ARG;
+    return mguarded(m, [&] { return multi_each(m, [&](sr_ctx* c, int) { return sr_set_option_impl(c, name, value); }); });
+}
+int sr_multi_run_streamed(sr_multi* m, int32_t n_taxa, int64_t n_sites, const uint8_t* states, int64_t pitch, int64_t site0,
+                          int64_t n, double* lnl, double* joint, sr_compact* compact, double threshold) {
+    if (!m) return SR_ERR_ARG;
+    return mguarded(m, [&] { return sr_multi_run_streamed_impl(m, n_taxa, n_sites, states, pitch, site0, n, lnl, joint, compact, threshold); });
+}
+
+// ---- the exported symbols: every entry point is fenced, nothing may unwind into a JVM (or any C caller)
+void sr_destroy(sr_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (int i = 0; i < 3; ++i) if (c->h_bounce[i]) cudaFreeHost(c->h_bounce[i]);
+    for (int i = 0; i < 3; ++i) {
+        if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+        if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+        if (c->ev_sfree[i]) cudaEventDestroy(c->ev_sfree[i]);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    delete c;
+}
+
+const char* sr_last_error(const sr_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+void* sr_host_alloc(size_t bytes) {
+    // portable: page-locked for every device, so one buffer can feed all the contexts of an sr_multi
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void sr_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+#ifdef SR_TIMELINE
+int sr_debug_timeline(sr_ctx* c, unsigned* out, int64_t n_words) {
+    return guarded(c, [&] { return sr_debug_timeline_impl(c, out, n_words); });
+}
+#endif
+
+int sr_create(sr_ctx** out, int device) {
+    return guarded(nullptr, [&] { return sr_create_impl(out, device); });
+}
+int sr_set_model(sr_ctx* c, const double* eval, const double* evec, const double* ievc, const double* pi) {
+    return guarded(c, [&] { return sr_set_model_impl(c, eval, evec, ievc, pi); });
+}
+int sr_set_rates(sr_ctx* c, int K, const double* rates) {
+    return guarded(c, [&] { return sr_set_rates_impl(c, K, rates); });
+}
+int sr_set_tree(sr_ctx* c, int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                const int32_t* leaf_row, int32_t root) {
+    return guarded(c, [&] { return sr_set_tree_impl(c, n_nodes, child_off, child_idx, blen, leaf_row, root); });
+}
+int sr_set_alignment(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* states, int64_t pitch) {
+    return guarded(c, [&] { return sr_set_alignment_impl(c, n_taxa, n_sites, states, pitch); });
+}
+int sr_run_device(sr_ctx* c, int64_t site0, int64_t n, double* d_lnl, double* d_joint, sr_compact* d_compact,
+                  double threshold, void* stream) {
+    return guarded(c, [&] { return sr_run_device_impl(c, site0, n, d_lnl, d_joint, d_compact, threshold, stream); });
+}
+int sr_run(sr_ctx* c, int64_t site0, int64_t n, double* lnl, double* joint, sr_compact* compact, double threshold) {
+    return guarded(c, [&] { return sr_run_impl(c, site0, n, lnl, joint, compact, threshold); });
+}
+int sr_run_streamed(sr_ctx* c, int32_t n_taxa, int64_t n_sites, const uint8_t* states, int64_t pitch, int64_t site0,
+                    int64_t n, double* lnl, double* joint, sr_compact* compact, double threshold) {
+    return guarded(c, [&] { return sr_run_streamed_impl(c, n_taxa, n_sites, states, pitch, site0, n, lnl, joint, compact, threshold); });
+}
+int sr_set_option(sr_ctx* c, const char* name, int64_t value) {
+    return guarded(c, [&] { return sr_set_option_impl(c, name, value); });
+}
+int sr_get_profile(sr_ctx* c, sr_profile* out) {
+    return guarded(c, [&] { return sr_get_profile_impl(c, out); });
+}
+int sr_profile_reset(sr_ctx* c) {
+    return guarded(c, [&] { return sr_profile_reset_impl(c); });
+}
+int sr_schedule_info(sr_ctx* c, int64_t* n_steps, int32_t* stack_depth, double* flops) {
+    return guarded(c, [&] { return sr_schedule_info_impl(c, n_steps, stack_depth, flops); });
+}
+int sr_schedule_dump(int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                     const int32_t* leaf_row, int32_t root, int32_t rescale_every, int32_t cherry_tables, int64_t cap_steps,
+                     int32_t* steps, int32_t* node_slot, int64_t* n_steps, int32_t* stack_depth) {
+    return guarded(nullptr, [&] { return sr_schedule_dump_impl(n_nodes, child_off, child_idx, blen, leaf_row, root, rescale_every, cherry_tables, cap_steps, steps, node_slot, n_steps, stack_depth); });
+}
+int sr_schedule_records(int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx, const double* blen,
+                     const int32_t* leaf_row, int32_t root, int32_t rescale_every, int32_t cherry_tables, int64_t cap_steps,
+                     uint32_t* crec, uint32_t* prec, int32_t* clade_gathers, int64_t* n_steps, int64_t* n_clade_gathers) {
+    return guarded(nullptr, [&] { return sr_schedule_records_impl(n_nodes, child_off, child_idx, blen, leaf_row, root, rescale_every, cherry_tables, cap_steps, crec, prec, clade_gathers, n_steps, n_clade_gathers); });
+}
+int sr_measure_fp64_peak(sr_ctx* c, double ms_target, double* tflops) {
+    return guarded(c, [&] { return sr_measure_fp64_peak_impl(c, ms_target, tflops); });
+}
+int sr_debug_pmatrix(sr_ctx* c, int32_t node, int32_t k, double* out) {
+    return guarded(c, [&] { return sr_debug_pmatrix_impl(c, node, k, out); });
+}
+int sr_debug_cherry_table(sr_ctx* c, int32_t node, int32_t k, double* out, int64_t cap_doubles, int32_t* n_rows) {
+    return guarded(c, [&] { return sr_debug_cherry_table_impl(c, node, k, out, cap_doubles, n_rows); });
+}
 
 }  // extern "C"

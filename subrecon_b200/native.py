@@ -25,7 +25,9 @@ _U8 = ctypes.POINTER(ctypes.c_uint8)
 EXPORTS = ["sr_create", "sr_destroy", "sr_last_error", "sr_set_model", "sr_set_rates", "sr_set_tree",
            "sr_set_alignment", "sr_run", "sr_run_device", "sr_run_streamed", "sr_host_alloc", "sr_host_free",
            "sr_set_option", "sr_get_profile", "sr_profile_reset", "sr_schedule_info", "sr_measure_fp64_peak",
-           "sr_debug_pmatrix", "sr_debug_cherry_table", "sr_schedule_dump"]
+           "sr_debug_pmatrix", "sr_debug_cherry_table", "sr_schedule_dump", "sr_schedule_records", "sr_compact_cap_for",
+           "sr_compact_stride", "sr_multi_create", "sr_multi_destroy", "sr_multi_last_error", "sr_multi_count", "sr_multi_ctx",
+           "sr_multi_set_model", "sr_multi_set_rates", "sr_multi_set_tree", "sr_multi_set_option", "sr_multi_run_streamed"]
 
 
 class SrError(RuntimeError):
@@ -43,6 +45,21 @@ class Compact(ctypes.Structure):
 COMPACT_DTYPE = np.dtype([("lnl", "<f8"), ("max_ii_prob", "<f8"), ("max_prob", "<f8"), ("n_kept", "<i4"),
                           ("interesting", "<i4"), ("pair", "<i2", (8,)), ("prob", "<f8", (8,))])
 assert COMPACT_DTYPE.itemsize == ctypes.sizeof(Compact)
+
+
+def compact_dtype(cap=8):
+    """numpy view of a compact record of capacity `cap` (include/subrecon_b200.h::sr_compact): 32-byte head, int16 pair[cap]
+    padded to 8 bytes, double prob[cap]. cap = 8 is `sr_compact` / COMPACT_DTYPE."""
+    cap = int(cap)
+    pb = (2 * cap + 7) // 8 * 8
+    return np.dtype({"names": ["lnl", "max_ii_prob", "max_prob", "n_kept", "interesting", "pair", "prob"],
+                     "formats": ["<f8", "<f8", "<f8", "<i4", "<i4", ("<i2", (cap,)), ("<f8", (cap,))],
+                     "offsets": [0, 8, 16, 24, 28, 32, 32 + pb], "itemsize": 32 + pb + 8 * cap})
+
+
+def compact_cap_for(threshold):
+    """Entries a compact record must hold so that `threshold` loses nothing: min(400, floor(1/threshold))."""
+    return int(lib().sr_compact_cap_for(float(threshold)))
 
 
 class Profile(ctypes.Structure):
@@ -101,17 +118,37 @@ def lib():
         L.sr_schedule_dump.argtypes = [ctypes.c_int32, _I32, _I32, _D, _I32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                        ctypes.c_int64, _I32, _I32, ctypes.POINTER(ctypes.c_int64),
                                        ctypes.POINTER(ctypes.c_int32)]
+        L.sr_compact_cap_for.argtypes = [ctypes.c_double]
+        L.sr_compact_stride.argtypes = [ctypes.c_int]
+        L.sr_compact_stride.restype = ctypes.c_size_t
+        L.sr_multi_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, _I32]
+        L.sr_multi_destroy.argtypes = [vp]
+        L.sr_multi_destroy.restype = None
+        L.sr_multi_last_error.argtypes = [vp]
+        L.sr_multi_last_error.restype = ctypes.c_char_p
+        L.sr_multi_count.argtypes = [vp]
+        L.sr_multi_ctx.argtypes = [vp, ctypes.c_int]
+        L.sr_multi_ctx.restype = vp
+        L.sr_multi_set_model.argtypes = [vp, _D, _D, _D, _D]
+        L.sr_multi_set_rates.argtypes = [vp, ctypes.c_int, _D]
+        L.sr_multi_set_tree.argtypes = [vp, ctypes.c_int32, _I32, _I32, _D, _I32, ctypes.c_int32]
+        L.sr_multi_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+        L.sr_multi_run_streamed.argtypes = [vp, ctypes.c_int32, ctypes.c_int64, vp, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_int64, vp, vp, vp, ctypes.c_double]
+        L.sr_schedule_records.argtypes = [ctypes.c_int32, _I32, _I32, _D, _I32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                          ctypes.c_int64, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), _I32,
+                                          ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
         _lib = L
     return _lib
 
 
-STEP_INTS = 12
+STEP_INTS = 16
 
 
 def schedule_dump(ft, rescale_every=8, cherry_tables=True):
-    """Host-only: the fused pruning schedule for a FlatTree -> (steps[n,12] int32, node_slot[n_nodes], stack_depth).
-    Step columns: word, alignment rows of gathers 0..2; second rows of the step's two clade gathers, their third rows;
-    first table row of each, 2 unused (include/subrecon_b200.h::sr_schedule_dump)."""
+    """Host-only: the fused pruning schedule for a FlatTree -> (steps[n,16] int32, node_slot[n_nodes], stack_depth).
+    Step columns: word, alignment rows of gathers 0..2; for a clade gather its second row (columns 4..6), its third row
+    (7..9) and its table's first row (10..12); 3 unused (include/subrecon_b200.h::sr_schedule_dump)."""
     off = np.ascontiguousarray(ft.child_off, dtype=np.int32)
     idx = np.ascontiguousarray(ft.child_idx, dtype=np.int32)
     bl = np.ascontiguousarray(ft.blen, dtype=np.float64)
@@ -127,6 +164,28 @@ def schedule_dump(ft, rescale_every=8, cherry_tables=True):
     if rc:
         raise SrError(rc, "sr_schedule_dump failed")
     return steps[:n.value].copy(), node_slot, depth.value
+
+
+def schedule_records(ft, rescale_every=8, cherry_tables=True):
+    """Host-only: the record streams `prune_kernel` reads (csrc/prune.cuh) -> (crec[n,4] uint32, prec[n,8] uint32,
+    clade_gathers[m,4] int32)."""
+    off = np.ascontiguousarray(ft.child_off, dtype=np.int32)
+    idx = np.ascontiguousarray(ft.child_idx, dtype=np.int32)
+    bl = np.ascontiguousarray(ft.blen, dtype=np.float64)
+    lr = np.ascontiguousarray(ft.leaf_row, dtype=np.int32)
+    cap = int(ft.n_nodes) + 8
+    crec = np.zeros((cap, 4), dtype=np.uint32)
+    prec = np.zeros((cap, 8), dtype=np.uint32)
+    cg = np.zeros((3 * cap, 4), dtype=np.int32)
+    n, m = ctypes.c_int64(), ctypes.c_int64()
+    u32 = ctypes.POINTER(ctypes.c_uint32)
+    rc = lib().sr_schedule_records(int(ft.n_nodes), off.ctypes.data_as(_I32), idx.ctypes.data_as(_I32), bl.ctypes.data_as(_D),
+                                   lr.ctypes.data_as(_I32), int(ft.root), int(rescale_every), int(bool(cherry_tables)), cap,
+                                   crec.ctypes.data_as(u32), prec.ctypes.data_as(u32), cg.ctypes.data_as(_I32),
+                                   ctypes.byref(n), ctypes.byref(m))
+    if rc:
+        raise SrError(rc, "sr_schedule_records failed")
+    return crec[:n.value].copy(), prec[:n.value].copy(), cg[:m.value].copy()
 
 
 class PinnedArray:
@@ -164,6 +223,7 @@ class Context:
         if rc:
             raise SrError(rc, (lib().sr_last_error(None) or b"").decode())
         self.device = device
+        self.compact_cap = 8
 
     def close(self):
         if self._h:
@@ -212,6 +272,8 @@ class Context:
 
     def set_option(self, name, value):
         self._ck(lib().sr_set_option(self._h, name.encode(), int(value)))
+        if name == "compact_cap":
+            self.compact_cap = int(value)
 
     def run(self, site0=0, n=None, want_joint=True, want_compact=False, threshold=0.5, out=None):
         """-> dict(lnl=[n], joint=[n,20,20]|None, compact=structured[n]|None); `out` may supply (pinned) arrays."""
@@ -220,7 +282,7 @@ class Context:
         out = out or {}
         lnl = out.get("lnl") if out.get("lnl") is not None else np.empty(n, dtype=np.float64)
         joint = (out.get("joint") if out.get("joint") is not None else np.empty((n, 20, 20), dtype=np.float64)) if want_joint else None
-        comp = (out.get("compact") if out.get("compact") is not None else np.zeros(n, dtype=COMPACT_DTYPE)) if want_compact else None
+        comp = (out.get("compact") if out.get("compact") is not None else np.zeros(n, dtype=compact_dtype(self.compact_cap))) if want_compact else None
         self._ck(lib().sr_run(self._h, int(site0), int(n), lnl.ctypes.data, joint.ctypes.data if want_joint else None,
                               comp.ctypes.data if want_compact else None, float(threshold)))
         return {"lnl": lnl, "joint": joint, "compact": comp}
@@ -234,7 +296,7 @@ class Context:
         out = out or {}
         lnl = out.get("lnl") if out.get("lnl") is not None else np.empty(n, dtype=np.float64)
         joint = (out.get("joint") if out.get("joint") is not None else np.empty((n, 20, 20), dtype=np.float64)) if want_joint else None
-        comp = (out.get("compact") if out.get("compact") is not None else np.zeros(n, dtype=COMPACT_DTYPE)) if want_compact else None
+        comp = (out.get("compact") if out.get("compact") is not None else np.zeros(n, dtype=compact_dtype(self.compact_cap))) if want_compact else None
         self._ck(lib().sr_run_streamed(self._h, st.shape[0], st.shape[1], st.ctypes.data, st.strides[0], int(site0), int(n),
                                        lnl.ctypes.data, joint.ctypes.data if want_joint else None,
                                        comp.ctypes.data if want_compact else None, float(threshold)))
@@ -276,3 +338,73 @@ class Context:
         n = ctypes.c_int32()
         self._ck(lib().sr_debug_cherry_table(self._h, int(node), int(rate_class), out.ctypes.data_as(_D), out.size, ctypes.byref(n)))
         return out[:n.value * 20].reshape((21, 21, 20) if n.value == 441 else (21, 21, 21, 20))
+
+
+class MultiContext:
+    """One host process driving every GPU of the box (include/subrecon_b200.h::sr_multi): the single-JVM route."""
+
+    def __init__(self, devices=None):
+        self._h = ctypes.c_void_p()
+        if devices is None:
+            rc = lib().sr_multi_create(ctypes.byref(self._h), 0, None)
+        else:
+            ids = np.ascontiguousarray(list(devices), dtype=np.int32)
+            rc = lib().sr_multi_create(ctypes.byref(self._h), int(ids.size), ids.ctypes.data_as(_I32))
+        if rc:
+            raise SrError(rc, (lib().sr_multi_last_error(None) or b"").decode())
+        self.compact_cap = 8
+
+    @property
+    def count(self):
+        return int(lib().sr_multi_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().sr_multi_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise SrError(rc, (lib().sr_multi_last_error(self._h) or b"").decode())
+
+    def set_model(self, Eval, Evec, Ievc, pi):
+        k = [Context._d(x) for x in (Eval, Evec, Ievc, pi)]
+        self._ck(lib().sr_multi_set_model(self._h, k[0][1], k[1][1], k[2][1], k[3][1]))
+
+    def set_rates(self, rates):
+        r, rp = Context._d(rates)
+        self._ck(lib().sr_multi_set_rates(self._h, int(r.size), rp))
+
+    def set_tree(self, ft):
+        off = np.ascontiguousarray(ft.child_off, dtype=np.int32)
+        idx = np.ascontiguousarray(ft.child_idx, dtype=np.int32)
+        bl = np.ascontiguousarray(ft.blen, dtype=np.float64)
+        lr = np.ascontiguousarray(ft.leaf_row, dtype=np.int32)
+        self._ck(lib().sr_multi_set_tree(self._h, int(ft.n_nodes), off.ctypes.data_as(_I32), idx.ctypes.data_as(_I32),
+                                         bl.ctypes.data_as(_D), lr.ctypes.data_as(_I32), int(ft.root)))
+
+    def set_option(self, name, value):
+        self._ck(lib().sr_multi_set_option(self._h, name.encode(), int(value)))
+        if name == "compact_cap":
+            self.compact_cap = int(value)
+
+    def run_streamed(self, states, site0=0, n=None, want_joint=True, want_compact=False, threshold=0.5, out=None):
+        st = states
+        if not (isinstance(st, np.ndarray) and st.dtype == np.uint8 and st.ndim == 2 and st.strides[1] == 1):
+            st = np.ascontiguousarray(states, dtype=np.uint8)
+        if n is None:
+            n = st.shape[1] - site0
+        out = out or {}
+        lnl = out.get("lnl") if out.get("lnl") is not None else np.empty(n, dtype=np.float64)
+        joint = (out.get("joint") if out.get("joint") is not None else np.empty((n, 20, 20), dtype=np.float64)) if want_joint else None
+        comp = (out.get("compact") if out.get("compact") is not None else np.zeros(n, dtype=compact_dtype(self.compact_cap))) if want_compact else None
+        self._ck(lib().sr_multi_run_streamed(self._h, st.shape[0], st.shape[1], st.ctypes.data, st.strides[0], int(site0), int(n),
+                                             lnl.ctypes.data, joint.ctypes.data if want_joint else None,
+                                             comp.ctypes.data if want_compact else None, float(threshold)))
+        return {"lnl": lnl, "joint": joint, "compact": comp}

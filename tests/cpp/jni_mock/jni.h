@@ -28,6 +28,7 @@ typedef const struct JNINativeInterface_ *JNIEnv;
 struct JNINativeInterface_ {
     jsize (*GetArrayLength)(JNIEnv *, jarray);
     void *(*GetDirectBufferAddress)(JNIEnv *, jobject);
+    jlong (*GetDirectBufferCapacity)(JNIEnv *, jobject);
     jdouble *(*GetDoubleArrayElements)(JNIEnv *, jdoubleArray, jboolean *);
     jint *(*GetIntArrayElements)(JNIEnv *, jintArray, jboolean *);
     const char *(*GetStringUTFChars)(JNIEnv *, jstring, jboolean *);

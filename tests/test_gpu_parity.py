@@ -26,8 +26,7 @@ def ctx():
     c.close()
 
 
-def setup(ctx, p, tile_m=2):
-    ctx.set_option("tile_m", tile_m)
+def setup(ctx, p):
     ctx.set_option("chunk_cols", 1 << 20)
     ctx.set_model(p.model.Eval, p.model.Evec, p.model.Ievc, p.model.pi)
     ctx.set_rates(p.rates)
@@ -43,11 +42,10 @@ def check(ctx, p, lnl, joint, **kw):
     return r
 
 
-@pytest.mark.parametrize("tile_m", [2, 4])
-def test_cfg1_lysozyme_vs_oracle_and_golden(ctx, example_problem, tile_m):
+def test_cfg1_lysozyme_vs_oracle_and_golden(ctx, example_problem):
     p = example_problem
     lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates)
-    setup(ctx, p, tile_m)
+    setup(ctx, p)
     r = check(ctx, p, lnl, joint)
     g = np.load(os.path.join(HERE, "golden", "lysozyme_golden.npz"))       # PAL-bytecode golden
     assert rel_err(r["lnl"], g["lnl"]) < TOL and rel_err(r["joint"], g["joint"]) < TOL
@@ -152,11 +150,10 @@ def test_cherry_tables_match_pal(ctx, example_problem):
         ctx.set_option("cherry_pitchforks", 1)
 
 
-@pytest.mark.parametrize("tile_m", [2, 4])
-def test_cfg2_full(ctx, tile_m):
+def test_cfg2_full(ctx):
     p = synthetic(2, 10_000)
     lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
-    setup(ctx, p, tile_m)
+    setup(ctx, p)
     check(ctx, p, lnl, joint)
 
 
@@ -214,7 +211,6 @@ def test_adversarial_underflow(ctx, shape):
         states[:, col] = rare[(np.arange(n) + rng.integers(0, 3)) % 3] if col % 2 else rare[rng.integers(0, 3, size=n)]
     lnl, joint = oracle.run(flat, states, model, rates)
     assert lnl.min() < -1500 and np.isfinite(lnl).all()
-    ctx.set_option("tile_m", 2)
     ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
     ctx.set_rates(rates)
     ctx.set_tree(flat)
@@ -270,18 +266,15 @@ def test_cfg5_full_size_properties(ctx):
 def test_cfg5_subset(ctx):
     p = synthetic(5, 2048)
     lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
-    setup(ctx, p, 4)
+    setup(ctx, p)
     check(ctx, p, lnl, joint)
 
 
-@pytest.mark.parametrize("opts", [dict(tile_m=4), dict(tile_m=4, realloc=1), dict(tile_m=4, realloc=1, rotate=0), dict(warps=8), dict(warps=15),
-                                  dict(warps=8, rotate=0), dict(holes=0), dict(holes=1), dict(holes=13), dict(holes=1234), dict(rotate=0),
-                                  dict(warps=11), dict(warps=11, rotate=0), dict(warps=11, holes=0), dict(warps=11, holes=0, rotate=0),
-                                  dict(warps=12), dict(warps=12, rotate=0),
-                                  dict(cherry_tables=0), dict(cherry_tables=0, warps=11), dict(cherry_tables=0, tile_m=4), dict(cherry_table_mb=1), dict(cherry_table_mb=40), dict(cherry_pairs=0), dict(cherry_pitchforks=0), dict(cherry_pitchforks=0, cherry_pairs=0),
-                                  dict(cherry_pairs=0, rotate=0)])
+@pytest.mark.parametrize("opts", [dict(k_fastest=1), dict(cherry_tables=0), dict(cherry_tables=0, k_fastest=1), dict(cherry_table_mb=1),
+                                  dict(cherry_table_mb=40), dict(cherry_pairs=0), dict(cherry_pitchforks=0),
+                                  dict(cherry_pitchforks=0, cherry_pairs=0), dict(rescale_every=1), dict(rescale_every=12)])
 def test_kernel_variants_agree(ctx, opts):
-    """Every tuning variant of the pruning kernel (sr_set_option) gives oracle-exact results."""
+    """Every schedule / work-order option of the pruning kernel (sr_set_option) gives oracle-exact results."""
     p = synthetic(3, 512)
     lnl, joint = oracle.run(p.flat, p.states, p.model, p.rates, threads=os.cpu_count())
     setup(ctx, p)
@@ -291,7 +284,7 @@ def test_kernel_variants_agree(ctx, opts):
         r = ctx.run()
         assert rel_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL
     finally:
-        for k, v in dict(tile_m=2, holes=2, rotate=1, cherry_tables=1, cherry_table_mb=4096, cherry_pairs=1, cherry_pitchforks=1).items():   # tile_m=2 restores the default warp layout
+        for k, v in dict(k_fastest=0, cherry_tables=1, cherry_table_mb=4096, cherry_pairs=1, cherry_pitchforks=1, rescale_every=8).items():
             ctx.set_option(k, v)
 
 
@@ -419,7 +412,6 @@ def test_polytomy_missing_data_custom_rates(ctx):
     for rates in (np.array([1.0]), np.array([0.3, 1.7]), np.array([0.0, 0.5, 2.5]), oracle.gamma_rates(8, 0.5),
                   oracle.gamma_rates(16, 0.7), oracle.gamma_rates(20, 1.3)):
         lnl, joint = oracle.run(flat, states, model, rates)
-        ctx.set_option("tile_m", 2)
         ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
         ctx.set_rates(rates)
         ctx.set_tree(flat)
@@ -452,7 +444,6 @@ def test_clade_table_shapes(ctx, newick):
     rates = oracle.gamma_rates(3, 0.8)
     lnl, joint = oracle.run(flat, states, model, rates)
     _, node_slot, _ = native.schedule_dump(flat)
-    ctx.set_option("tile_m", 2)
     ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
     ctx.set_rates(rates)
     ctx.set_tree(flat)
@@ -486,14 +477,12 @@ def test_random_trees_fuzz(ctx):
         model = oracle.OracleModel(["WAG", "JTT", "Dayhoff", "BLOSUM62"][it % 4])
         rates = oracle.gamma_rates(K, 0.6) if K > 1 else np.array([1.0])
         lnl, joint = oracle.run(flat, states, model, rates)
-        ctx.set_option("tile_m", 2 if it % 5 else 4)
         ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
         ctx.set_rates(rates)
         ctx.set_tree(flat)
         ctx.set_alignment(states)
         r = ctx.run()
         assert lnl_err(r["lnl"], lnl) < TOL and rel_err(r["joint"], joint) < TOL, (it, tree.to_newick())
-    ctx.set_option("tile_m", 2)
 
 
 def test_leaf_as_root_child(ctx):
@@ -523,7 +512,6 @@ def test_degenerate_shapes(ctx):
     flat = treeio.flatten_tree(tree)
     states = treeio.encode_alignment(["AR-W", "AK-C"])
     lnl, joint = oracle.run(flat, states, model, np.array([1.0]))
-    ctx.set_option("tile_m", 2)
     ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
     ctx.set_rates(np.array([1.0]))
     ctx.set_tree(flat)
@@ -606,8 +594,10 @@ def test_error_behaviour(ctx, example_problem):
     with pytest.raises(native.SrError, match="taxa"):
         fresh.set_alignment(p.states[:5])
         fresh.run()
+    with pytest.raises(native.SrError, match="unknown option"):
+        fresh.set_option("tile_m", 4)                                     # round-1 tuning variants are gone
     with pytest.raises(native.SrError):
-        fresh.set_option("tile_m", 3)
+        fresh.set_option("rescale_every", 13)                             # beyond the tested underflow bound
     fresh.close()
     with pytest.raises(native.SrError):
         native.Context(99)

@@ -6,8 +6,7 @@ from helpers import synthetic
 from subrecon_b200 import native
 p = synthetic(3, 4096)
 ctx = native.Context(0)
-for tm in (2, 4):
-    ctx.set_option("tile_m", tm)
+for tm in (2,):
     ctx.set_model(p.model.Eval, p.model.Evec, p.model.Ievc, p.model.pi); ctx.set_rates(p.rates); ctx.set_tree(p.flat)
     for reps in (4, 64, 256):
         big = np.tile(p.states, (1, reps))
@@ -22,7 +21,7 @@ for tm in (2, 4):
                 d = np.abs(l[bad] - ref[bad]) / np.abs(ref[bad])
                 print("   rel diff min/median/max", d.min(), np.median(d), d.max())
                 print("   first bad cols", bad[:20], " mod 128:", (bad[:20] % 128), " tile:", bad[:20] // 128)
-                S = 128 if tm == 2 else 256
+                S = 192
                 print("   distinct tiles with errors:", np.unique(bad // S).size, "of", l.size // S, "; hist of col-in-tile//8:", np.bincount((bad % S) // 8, minlength=S // 8))
                 # is the base block itself consistent between trials?
         r2 = ctx.run(want_joint=False)

@@ -1,5 +1,5 @@
 """Small fixed workload for ncu / timing experiments: config #3 tree, `--cols` columns resident, a few launches.
-Usage: python tools/prune_probe.py [--cols 131072] [--tile-m 2] [--reps 3] [--taxa 1000]"""
+Usage: python tools/prune_probe.py [--cols 131072] [--reps 3] [--taxa 1000] [--tree yule|balanced|caterpillar] [--tables 0|1]"""
 import argparse
 import os
 import sys
@@ -12,13 +12,10 @@ from subrecon_b200 import native, palmodel, synth, treeio  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--cols", type=int, default=131072)
-ap.add_argument("--tile-m", type=int, default=2)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--warps", type=int, default=0)
-ap.add_argument("--holes", type=int, default=-1)
-ap.add_argument("--rotate", type=int, default=-1)
 ap.add_argument("--rescale", type=int, default=0)
-ap.add_argument("--debug", type=int, default=0)
+ap.add_argument("--k-fastest", type=int, default=-1)
+ap.add_argument("--tables", type=int, default=1)
 ap.add_argument("--taxa", type=int, default=1000)
 ap.add_argument("--tree", default="yule")
 ap.add_argument("--ncat", type=int, default=4)
@@ -37,19 +34,11 @@ else:
     base = synth.simulate_alignment(tree, model, rates, 4096, seed=103)
 states = np.tile(base, (1, (a.cols + 4095) // 4096))[:, :a.cols]
 ctx = native.Context(0)
-ctx.set_option("tile_m", a.tile_m)
-if a.holes >= 0:
-    ctx.set_option("holes", a.holes)
 if a.rescale:
     ctx.set_option("rescale_every", a.rescale)
-if a.rotate >= 0:
-    ctx.set_option("rotate", a.rotate)
-if a.warps == 13:
-    ctx.set_option("realloc", 1)
-elif a.warps:
-    ctx.set_option("warps", a.warps)
-if a.debug:
-    ctx.set_option("debug", a.debug)
+if a.k_fastest >= 0:
+    ctx.set_option("k_fastest", a.k_fastest)
+ctx.set_option("cherry_tables", a.tables)
 ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
 ctx.set_rates(rates)
 ctx.set_tree(treeio.flatten_tree(tree))
@@ -63,5 +52,5 @@ for _ in range(a.reps):
 p = ctx.profile(reset=True)
 ms = p["ms_prune"] / p["n_prune"]
 tf = info["flops_per_column_rate"] * len(rates) * a.cols / ms * 1e-9
-print(f"tree={a.tree} taxa={a.taxa} cols={a.cols} tile_m={a.tile_m} warps={a.warps} holes={a.holes} rotate={a.rotate} K={a.ncat} depth={info['stack_depth']} steps={info['n_steps']}: "
+print(f"tree={a.tree} taxa={a.taxa} cols={a.cols} tables={a.tables} k_fastest={a.k_fastest} K={a.ncat} depth={info['stack_depth']} steps={info['n_steps']}: "
       f"prune {ms:.3f} ms/launch  {a.cols / ms * 1e-3:.3f} Mcol/s  {tf:.2f} TFLOP/s  root {p['ms_root'] / p['n_root']:.3f} ms")

@@ -1,7 +1,7 @@
 """Per-warp clock stamps of the pruning kernel's step phases on one SM (instrumented build, -DSR_TIMELINE).
 
 Build here (no GPU needed):  python tools/timeline.py --build
-Run on the GPU box:          SUBRECON_B200_LIB=tools/_build/libsubrecon_tl.so python tools/timeline.py [--warps 11] [--realloc 1]
+Run on the GPU box:          SUBRECON_B200_LIB=tools/_build/libsubrecon_tl.so python tools/timeline.py [--tables 0]
 Stamps per step and warp: 0 step begins, 1 stage landed, 2 ready to burst, 3 burst starts (after the rotation barrier),
 4 last DMMA issued, 5 stage released, 6 epilogue issued, 7 step ends.
 """
@@ -17,11 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TL_LIB = os.path.join(ROOT, "tools", "_build", "libsubrecon_tl.so")
 ap = argparse.ArgumentParser()
 ap.add_argument("--build", action="store_true")
-ap.add_argument("--tile-m", type=int, default=2)
-ap.add_argument("--warps", type=int, default=0)
-ap.add_argument("--realloc", type=int, default=0)
-ap.add_argument("--rotate", type=int, default=-1)
-ap.add_argument("--holes", type=int, default=-1)
+ap.add_argument("--tables", type=int, default=1)
 ap.add_argument("--cols", type=int, default=148 * 192 * 2)
 ap.add_argument("--first", type=int, default=200, help="first step of the analysed window")
 ap.add_argument("--steps", type=int, default=600, help="steps in the analysed window")
@@ -45,15 +41,7 @@ rates = palmodel.gamma_rates(4, 0.5)
 base = synth.simulate_alignment(tree, model, rates, 4096, seed=103)
 states = np.tile(base, (1, (a.cols + 4095) // 4096))[:, :a.cols]
 ctx = native.Context(0)
-ctx.set_option("tile_m", a.tile_m)
-if a.warps:
-    ctx.set_option("warps", a.warps)
-if a.realloc:
-    ctx.set_option("realloc", 1)
-if a.rotate >= 0:
-    ctx.set_option("rotate", a.rotate)
-if a.holes >= 0:
-    ctx.set_option("holes", a.holes)
+ctx.set_option("cherry_tables", a.tables)
 ctx.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
 ctx.set_rates(rates)
 ctx.set_tree(treeio.flatten_tree(tree))
