@@ -3,18 +3,26 @@
 
     python bench.py --gpus N --steps K --warmup W            # product arm (CUDA, through the C ABI)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU algorithm on host cores
+    python bench.py --config 4                                # BASELINE configs 1..5 (default 3, the headline)
+    python bench.py --config 5 --scaling strong --gpus 8      # fixed total size, contiguous column blocks per rank
 
-A "step" is one pass of the hot path (P matrices -> pruning -> root-branch joint) over one batch of synthetic
-alignment columns: BASELINE config #3, 1,000 taxa x 1,000,000 sites, WAG, K=4, alpha=0.5, Yule tree (seed 3).
-Weak scaling: every rank (one process per GPU) owns a block of that size; columns never interact, so there is no
-data-path collective — only the barrier, the max-over-ranks of the time and a reduce of the total lnL.
+A "step" is one pass of the hot path (P matrices -> clade tables -> pruning -> root-branch joint) over one batch of
+synthetic alignment columns. Default = BASELINE config #3: 1,000 taxa x 1,000,000 sites, WAG, K=4, alpha=0.5, Yule tree
+(seed 3), weak scaling (every rank owns a block of that size). Columns never interact, so there is no data-path
+collective — only the barrier, the max-over-ranks of the time and a reduce of the total lnL.
 
-  value   whole-job columns/s with the alignment resident in HBM and results left in HBM (CUDA events)
-  e2e     the same metric through sr_run_streamed with HOST buffers: pinned states H2D and lnl+400 probabilities
-          D2H inside the timed region, pipelined in column chunks
+  value     whole-job columns/s with the alignment resident in HBM and results (lnl + 400 probabilities) left in HBM
+            (CUDA events on the launching stream)
+  e2e       the same metric through the call a host makes, with HOST buffers: pinned states H2D and the per-column
+            result D2H inside the timed region. The result is the COMPACT record at the reference's default -threshold
+            0.5 — everything SiteResult keeps of a column (recon/SiteResult.java:55,69-83), 112 B — which is what the Java
+            integration reads (java/subrecon/recon/NativeRecon.java). One process per GPU (torchrun).
+  e2e_single_process   the same through sr_multi_run_streamed: ONE host process (rank 0) drives all N GPUs, the route a
+            single JVM takes; the other ranks idle meanwhile
+  e2e_full_joint       the same with all 400 probabilities per column coming back (3 208 B/column): bound by the host's
+            D2H ingest on multi-GPU boxes; `host_d2h_ceiling` is that limit measured in the same run
   roofline  the pruning kernel's algorithmic FP64 flops (K*(820*E_int + 20*E_leaf + 1200) per column) over
             its CUDA-event time, against the FP64 tensor-pipe (DMMA) peak probed live on the same GPU
-            (MEASURED_PEAKS.json has no FP64 entry; see profiles/fp64_peak_r01.json)
   cpu_baseline  the oracle's jar-faithful work mode (what PAL 1.51 really executes per column) on all host cores, on a
                 bounded sample of the same workload
 """
@@ -36,6 +44,21 @@ sys.path.insert(0, ROOT)
 METRIC = "alignment_columns_per_sec"
 UNIT = "columns/s"
 
+# BASELINE.json configs. `base` = simulated columns that are tiled up to `columns`.
+CONFIGS = {
+    1: dict(label="example/ primate lysozyme (19 taxa x 130 sites), WAG + mle.wag.freqs, K=4", kind="example", ncat=4, model="wag"),
+    2: dict(label="synthetic 100 taxa x 10k sites, JTT, K=4, balanced tree", taxa=100, columns=10_000, model="jtt", ncat=4,
+            tree="balanced", tree_seed=2, aln_seed=102, base=10_000),
+    3: dict(label="synthetic 1,000 taxa x 1M sites, WAG, K=4, Yule tree seed 3", taxa=1000, columns=1_000_000, model="wag", ncat=4,
+            tree="yule", tree_seed=3, aln_seed=103, base=8192),
+    4: dict(label="synthetic 5,000-taxon caterpillar x 200k sites, BLOSUM62, K=8, custom -pi", taxa=5000, columns=200_000,
+            model="blosum62", ncat=8, tree="caterpillar", tree_seed=4, aln_seed=104, base=1024, custom_pi=True),
+    5: dict(label="synthetic 2,000 taxa x 8M sites, Dayhoff, K=4, Yule tree seed 5", taxa=2000, columns=8_000_000, model="dayhoff",
+            ncat=4, tree="yule", tree_seed=5, aln_seed=105, base=4096),
+}
+TREES = {"yule": "yule_tree", "balanced": "balanced_tree", "caterpillar": "caterpillar_tree"}
+ORACLE_MODEL = {"wag": "WAG", "jtt": "JTT", "dayhoff": "Dayhoff", "blosum62": "BLOSUM62"}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -43,33 +66,104 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--taxa", type=int, default=1000)
-    ap.add_argument("--columns", type=int, default=1_000_000, help="columns per GPU")
-    ap.add_argument("--model", default="wag")
-    ap.add_argument("--ncat", type=int, default=4)
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU gets the config's column count; strong: the config's columns are split over the GPUs")
+    ap.add_argument("--columns", type=int, default=0, help="override the config's column count")
     ap.add_argument("--alpha", type=float, default=0.5)
     ap.add_argument("--chunk-cols", type=int, default=0, help="0 = library default")
+    ap.add_argument("--distinct", action="store_true", help="simulate every column (no tiling of a base block)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-joint", action="store_true", help="skip the 3 208 B/column end-to-end variant")
+    ap.add_argument("--no-single-process", action="store_true", help="skip the one-process-N-GPUs end-to-end variant")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
 
-def workload_config(a):
-    return {"workload": f"BASELINE config #3: synthetic {a.taxa} taxa x {a.columns} sites per GPU, {a.model.upper()}, "
-                        f"K={a.ncat}, alpha={a.alpha}, Yule tree seed 3, columns simulated down the tree (8192 distinct, tiled)",
-            "taxa": a.taxa, "columns_per_gpu": a.columns, "model": a.model, "rate_classes": a.ncat, "alpha": a.alpha,
-            "l2_policy": "inputs larger than L2: 1 GB of states in, 3.2 GB of results out per step (L2 = 126 MB)",
+def config_of(a):
+    c = dict(CONFIGS[a.config])
+    if a.columns:
+        c["columns"] = a.columns
+    return c
+
+
+def workload_config(a, c, columns_per_gpu, world):
+    data = ("the reference's own example alignment" if c.get("kind") == "example" else
+            f"columns simulated down the tree ({'all distinct' if a.distinct else str(min(c['base'], c['columns'])) + ' distinct, tiled'})")
+    big = columns_per_gpu * c.get("taxa", 19) > 2 ** 28
+    return {"workload": f"BASELINE config #{a.config}: {c['label']}, alpha={a.alpha}; {data}",
+            "baseline_config": a.config, "taxa": c.get("taxa", 19),
+            "columns_total": columns_per_gpu * world if a.scaling == "weak" else c["columns"],
+            "columns_per_gpu": columns_per_gpu, "model": c["model"], "rate_classes": c["ncat"], "alpha": a.alpha,
+            "l2_policy": ("inputs larger than L2: the state matrix and the result arrays of one step are each far beyond the 126 MB L2"
+                          if big else "correctness-sized config: its inputs fit in L2"),
             "parallelism": "columns sharded in contiguous blocks, one process per GPU, no data-path collective"}
 
 
-def make_problem(a, seed_shift=0):
+def make_model(a, c):
+    from subrecon_b200 import palmodel
+    freqs = None
+    if c.get("custom_pi"):
+        freqs = palmodel.normalise_cli_frequencies(np.random.default_rng(4).dirichlet(5.0 * np.ones(20)))
+    elif c.get("kind") == "example":
+        ex = os.path.join(ROOT, "tests", "golden", "example")
+        freqs = palmodel.normalise_cli_frequencies(open(os.path.join(ex, "freqs")).read().strip().split(","))
+    model = palmodel.host_model(c["model"], freqs)
+    model.custom_frequencies = freqs is not None
+    return model
+
+
+def make_tree(c):
+    from subrecon_b200 import synth, treeio
+    if c.get("kind") == "example":
+        return treeio.read_tree(os.path.join(ROOT, "tests", "golden", "example", "root.tre"))
+    return getattr(synth, TREES[c["tree"]])(c["taxa"], seed=c["tree_seed"])
+
+
+def make_problem(a, c, seed_shift=0):
+    """-> (tree, flat, model, rates, base states [taxa][base columns])"""
     from subrecon_b200 import palmodel, synth, treeio
-    tree = synth.yule_tree(a.taxa, seed=3)
-    model = palmodel.host_model(a.model)
-    rates = palmodel.gamma_rates(a.ncat, a.alpha)
-    base = synth.simulate_alignment(tree, model, rates, min(8192, a.columns), seed=103 + seed_shift)
+    rates = palmodel.gamma_rates(c["ncat"], a.alpha)
+    model = make_model(a, c)
+    tree = make_tree(c)
+    if c.get("kind") == "example":
+        names, seqs = treeio.read_fasta(os.path.join(ROOT, "tests", "golden", "example", "prot.fasta"))
+        c.setdefault("columns", len(seqs[0]))
+        c.setdefault("base", len(seqs[0]))
+        return tree, treeio.flatten_tree(tree, {n: i for i, n in enumerate(names)}), model, rates, treeio.encode_alignment(seqs)
+    base = synth.simulate_alignment(tree, model, rates, min(c["base"], c["columns"]), seed=c["aln_seed"] + seed_shift)
     return tree, treeio.flatten_tree(tree), model, rates, base
+
+
+def _sim_block(job):
+    cfg, alpha, n, seed = job
+    from subrecon_b200 import palmodel, synth
+
+    class A:
+        pass
+    a = A()
+    a.alpha = alpha
+    c = dict(CONFIGS[cfg])
+    return synth.simulate_alignment(make_tree(c), make_model(a, c), palmodel.gamma_rates(c["ncat"], alpha), n, seed=seed)
+
+
+def fill_states(a, c, dst, base, rank, world):
+    """dst[taxa][L] <- the base block tiled, or (--distinct) L columns each simulated down the tree (host cores in parallel)."""
+    L = dst.shape[1]
+    if not a.distinct or c.get("kind") == "example":
+        for c0 in range(0, L, base.shape[1]):
+            w = min(base.shape[1], L - c0)
+            dst[:, c0:c0 + w] = base[:, :w]
+        return
+    import multiprocessing as mp
+    blk = 16384
+    starts = list(range(0, L, blk))
+    jobs = [(a.config, a.alpha, min(blk, L - c0), 1_000_003 * (rank + 1) + c0) for c0 in starts]
+    procs = max(1, min(len(jobs), (os.cpu_count() or 2) // max(1, world)))
+    with mp.get_context("spawn").Pool(procs) as pool:
+        for c0, part in zip(starts, pool.imap(_sim_block, jobs)):
+            dst[:, c0:c0 + part.shape[1]] = part
 
 
 class ClockSampler(threading.Thread):
@@ -116,8 +210,8 @@ def bind_to_gpu_numa_node(local):
             return None
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus += list(range(int(a), int(b or a) + 1))
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
         allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
         if allowed:
             os.sched_setaffinity(0, allowed)
@@ -127,18 +221,19 @@ def bind_to_gpu_numa_node(local):
     return None
 
 
-def cpu_reference_run(a, columns, threads, mode, flat, model_name, rates, states):
-    """Time the oracle (the CPU restatement of the reference's per-column task) on `columns` columns."""
+def cpu_reference_run(columns, threads, mode, flat, model, model_name, rates, states):
+    """Time the oracle (the CPU restatement of the reference's per-column task) on `columns` columns. The oracle builds its
+    own model from PAL's tables and the same frequencies the product arm was given."""
     from oracle import oracle
-    om = oracle.OracleModel({"wag": "WAG", "jtt": "JTT", "dayhoff": "Dayhoff", "blosum62": "BLOSUM62"}[model_name])
+    om = oracle.OracleModel(ORACLE_MODEL[model_name], np.asarray(model.pi) if getattr(model, "custom_frequencies", False) else None)
     t0 = time.perf_counter()
-    oracle.run(flat, states[:, :columns], om, rates, mode=mode, threads=threads, want_joint=True)
+    oracle.run(flat, np.ascontiguousarray(states[:, :columns]), om, rates, mode=mode, threads=threads, want_joint=True)
     return time.perf_counter() - t0
 
 
-def calibrate_cpu_sample(a, threads, mode, flat, rates, states, target_s):
-    n = threads
-    dt = cpu_reference_run(a, n, threads, mode, flat, a.model, rates, states)
+def calibrate_cpu_sample(threads, mode, flat, model, model_name, rates, states, target_s):
+    n = min(threads, states.shape[1])
+    dt = cpu_reference_run(n, threads, mode, flat, model, model_name, rates, states)
     per_round = max(dt, 1e-3)                       # `threads` columns take ~per_round seconds
     rounds = max(1, int(target_s / per_round))
     return min(states.shape[1], n * rounds)
@@ -148,22 +243,25 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    tree, flat, model, rates, base = make_problem(a)
+    c = config_of(a)
+    tree, flat, model, rates, base = make_problem(a, c)
     threads = os.cpu_count() or 1
-    sample = calibrate_cpu_sample(a, threads, 2, flat, rates, base, target_s=max(2.0, 40.0 / max(1, a.steps + a.warmup)))
+    sample = calibrate_cpu_sample(threads, 2, flat, model, c["model"], rates, base, target_s=max(2.0, 40.0 / max(1, a.steps + a.warmup)))
     for _ in range(a.warmup):
-        cpu_reference_run(a, sample, threads, 2, flat, a.model, rates, base)
+        cpu_reference_run(sample, threads, 2, flat, model, c["model"], rates, base)
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        cpu_reference_run(a, sample, threads, 2, flat, a.model, rates, base)
+        cpu_reference_run(sample, threads, 2, flat, model, c["model"], rates, base)
     dt = time.perf_counter() - t0
     v = sample * a.steps / dt
     desc = (f"{sample} columns of the workload per step; oracle work mode 2 = per column, per edge, per rate class: rate-matrix "
             f"rebuild + elmhes/eltran/hqr2/luinverse + 20^3 P product, as PAL 1.51 executes it (SURVEY B.2); C port, -O2, "
             f"no JVM in this image")
+    cols, world = c["columns"], max(1, a.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a),
+            "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": a.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic" if c.get("kind") != "example" else "reference example files",
+            "config": workload_config(a, c, cols if a.scaling == "weak" else -(-cols // world), world),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -173,7 +271,7 @@ def run_reference(a):
 def run_b200(a):
     import torch
     import torch.distributed as dist
-    from subrecon_b200 import native
+    from subrecon_b200 import native, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -183,10 +281,12 @@ def run_b200(a):
     torch.cuda.set_device(local)
     affinity0 = os.sched_getaffinity(0)
     numa_node = bind_to_gpu_numa_node(local)          # page-locked buffers land on the GPU's NUMA node (first touch)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")     # host-side rendezvous that leaves the GPUs idle (single-process leg)
 
     def barrier():
         if world > 1:
@@ -200,8 +300,12 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    tree, flat, model, rates, base = make_problem(a, seed_shift=rank)
-    L, N = a.columns, base.shape[0]
+    c = config_of(a)
+    tree, flat, model, rates, base = make_problem(a, c, seed_shift=rank)
+    L_total = c["columns"]
+    L = sharding.column_block(L_total, world, rank)[1] if a.scaling == "strong" else L_total
+    N = base.shape[0]
+    total_columns = L_total if a.scaling == "strong" else L * world
     ctx = native.Context(local)
     if a.chunk_cols:
         ctx.set_option("chunk_cols", a.chunk_cols)
@@ -210,7 +314,7 @@ def run_b200(a):
     ctx.set_tree(flat)
     info = ctx.schedule_info()
     flops_per_col = info["flops_per_column_rate"] * len(rates)
-    # Cherry tables: a collapsed cherry's two tip products and its 20x20 contraction (2*20 + 820 algorithmic flops per
+    # Clade tables: a collapsed cherry's two tip products and its 20x20 contraction (2*20 + 820 algorithmic flops per
     # column and rate class) are replaced by one 20-flop gather product. `achieved` below stays ALGORITHMIC (SURVEY
     # §8d: what the reference's arithmetic costs); `executed` counts only what the kernel still computes per column.
     _, node_slot, _ = native.schedule_dump(flat)
@@ -225,11 +329,8 @@ def run_b200(a):
 
     # host (pinned) copies of the step's inputs and outputs
     h_states = native.PinnedArray((N, L), np.uint8)
-    for c0 in range(0, L, base.shape[1]):
-        w = min(base.shape[1], L - c0)
-        h_states.array[:, c0:c0 + w] = base[:, :w]
+    fill_states(a, c, h_states.array, base, rank, world)
     h_lnl = native.PinnedArray(L, np.float64)
-    h_joint = native.PinnedArray((L, 20, 20), np.float64)
 
     # ---- value: alignment resident in HBM, results stay in HBM
     ctx.set_alignment(h_states.array)
@@ -239,7 +340,7 @@ def run_b200(a):
     stream = tstream.cuda_stream                       # events below are recorded on it
 
     def step_resident():
-        ctx.set_rates(rates)            # marks the matrices dirty: K1 runs inside every step
+        ctx.set_rates(rates)            # marks the matrices dirty: K1 + K1b run inside every step
         ctx.run_device(0, L, d_lnl.data_ptr(), d_joint.data_ptr(), None, 0.5, stream)
 
     for _ in range(a.warmup):
@@ -259,7 +360,7 @@ def run_b200(a):
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     prof = ctx.profile(reset=True)
     ctx.set_option("profile", 0)
-    value = world * L * a.steps / (ms * 1e-3)
+    value = total_columns * a.steps / (ms * 1e-3)
     total_lnl = float(d_lnl.sum().item())
     if world > 1:
         t = torch.tensor([total_lnl], dtype=torch.float64, device="cuda")
@@ -268,78 +369,137 @@ def run_b200(a):
     k2_ms = prof["ms_prune"] / max(1, prof["n_prune"])
     k2_cols = prof["columns_pruned"] / max(1, prof["n_prune"])
     achieved = flops_per_col * k2_cols / (k2_ms * 1e-3) * 1e-12
-    launches = int(prof["n_pbuild"] + prof["n_prune"] + prof["n_root"])
+    launches = int(prof["n_pbuild"] + prof["n_prune"] + prof["n_root"] + prof["n_index"])
+    d_lnl_host = d_lnl.cpu().numpy()
+    del d_joint
+    torch.cuda.empty_cache()
 
-    # ---- e2e: host buffers, H2D + D2H inside the timed region, through the C ABI call a host makes
-    e2e = None
-    if not a.no_e2e:
-        out = {"lnl": h_lnl.array, "joint": h_joint.array}
-
-        def step_e2e():
-            ctx.set_rates(rates)
-            ctx.run_streamed(h_states.array, 0, L, want_joint=True, out=out)
-
-        for _ in range(max(1, min(a.warmup, 2))):
-            step_e2e()
+    def time_e2e(step, warm):
+        for _ in range(warm):
+            step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(a.steps):
-            step_e2e()
+            step()
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         barrier()
-        e2e = {"value": world * L * a.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(N) * L,
-               "d2h_bytes_per_step": L * (8 + 3200), "ms_per_step": dt / a.steps * 1e3,
-               "call": "sr_run_streamed (pinned host states in; lnl + 400 joint probabilities per column out)",
-               "bit_identical_to_resident": bool(np.array_equal(h_lnl.array, d_lnl.cpu().numpy())) and
-                                            bool(np.array_equal(h_joint.array[:4096].reshape(-1, 400), d_joint[:4096].cpu().numpy()))}
+        return dt
 
-    # ---- e2e, compact result: what the reference's SiteResult keeps per column (lnL, maxII, max, entries >= threshold;
-    #      recon/SiteResult.java:55,69-83) at the default -threshold 0.5 — 112 B instead of 3 208 B per column back to the host
-    e2e_compact = None
+    # ---- e2e: host buffers, H2D + D2H inside the timed region, through the C ABI call a host makes; the compact record
+    #      at the default -threshold 0.5 is the result the reference's consumer keeps (SiteResult.java:55,69-83)
+    e2e = e2e_full = e2e_single = None
+    comp_dtype = native.compact_dtype(8)
+    comp_ref = None
     if not a.no_e2e:
-        h_comp = native.PinnedArray(L, native.COMPACT_DTYPE)
+        h_comp = native.PinnedArray(L, comp_dtype)
         outc = {"lnl": h_lnl.array, "compact": h_comp.array}
 
-        def step_e2e_compact():
+        def step_e2e():
             ctx.set_rates(rates)
             ctx.run_streamed(h_states.array, 0, L, want_joint=False, want_compact=True, threshold=0.5, out=outc)
 
-        step_e2e_compact()
+        dtc = time_e2e(step_e2e, max(1, min(a.warmup, 2)))
+        e2e = {"value": total_columns * a.steps / dtc, "unit": UNIT, "h2d_bytes_per_step": int(N) * L,
+               "d2h_bytes_per_step": L * (8 + comp_dtype.itemsize), "ms_per_step": dtc / a.steps * 1e3,
+               "call": "sr_run_streamed, one process per GPU: pinned host states in; lnl + compact record (lnl, maxII, max, entries >= "
+                       "0.5: what SiteResult keeps) per column out",
+               "threshold": 0.5, "lnl_bit_identical_to_resident": bool(np.array_equal(h_comp.array["lnl"], d_lnl_host))}
+        comp_ref = h_comp.array[:min(L, 65536)].copy()
+        h_comp.free()
+
+    # ---- the same with all 400 probabilities coming back, and the host's D2H ceiling next to it
+    if not a.no_e2e and not a.no_full_joint:
+        h_joint = native.PinnedArray((L, 20, 20), np.float64)
+        out = {"lnl": h_lnl.array, "joint": h_joint.array}
+
+        def step_full():
+            ctx.set_rates(rates)
+            ctx.run_streamed(h_states.array, 0, L, want_joint=True, out=out)
+
+        dt = time_e2e(step_full, 1)
+        # every rank drains a device buffer into its pinned result array at the same time: what the host can ingest
+        nbytes = int(min(h_joint.array.nbytes, 1 << 30))
+        src = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        dst = torch.from_numpy(h_joint.array.reshape(-1).view(np.uint8)[:nbytes])
+        dst.copy_(src)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(a.steps):
-            step_e2e_compact()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
         torch.cuda.synchronize()
-        dtc = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        e2e_compact = {"value": world * L * a.steps / dtc, "unit": UNIT, "h2d_bytes_per_step": int(N) * L,
-                       "d2h_bytes_per_step": L * (8 + native.COMPACT_DTYPE.itemsize), "ms_per_step": dtc / a.steps * 1e3,
-                       "lnl_identical_to_full": bool(np.array_equal(h_comp.array["lnl"], d_lnl.cpu().numpy()))}
+        dtp = max_over_ranks(time.perf_counter() - t0)
+        ceiling = world * 4 * nbytes / dtp
+        e2e_full = {"value": total_columns * a.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(N) * L,
+                    "d2h_bytes_per_step": L * (8 + 3200), "ms_per_step": dt / a.steps * 1e3,
+                    "call": "sr_run_streamed with joint output: lnl + 400 joint probabilities per column out",
+                    "host_d2h_ceiling": {"GB_per_s_all_ranks": ceiling * 1e-9, "columns_per_s": ceiling / 3208.0,
+                                         "how": f"{world} rank(s) each copying {nbytes >> 20} MiB device->pinned host 4x concurrently"},
+                    "bit_identical_to_resident": bool(np.array_equal(h_lnl.array, d_lnl_host))}
+        del src, dst
+        h_joint.free()
+
+    # ---- one host process drives all N GPUs (sr_multi_*: the route a single JVM takes); ranks > 0 idle on the host meanwhile
+    if not a.no_e2e and not a.no_single_process:
+        if world > 1:
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                Lm = total_columns
+                m = native.MultiContext(list(range(world)))
+                m.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
+                m.set_rates(rates)
+                m.set_tree(flat)
+                ms_states = h_states if world == 1 else native.PinnedArray((N, Lm), np.uint8)
+                if world > 1:
+                    fill_states(a, c, ms_states.array, base, 0, 1)
+                ms_lnl = native.PinnedArray(Lm, np.float64)
+                ms_comp = native.PinnedArray(Lm, comp_dtype)
+                outm = {"lnl": ms_lnl.array, "compact": ms_comp.array}
+
+                def step_multi():
+                    m.set_rates(rates)
+                    m.run_streamed(ms_states.array, 0, Lm, want_joint=False, want_compact=True, threshold=0.5, out=outm)
+
+                step_multi()
+                t0 = time.perf_counter()
+                for _ in range(a.steps):
+                    step_multi()
+                dtm = time.perf_counter() - t0
+                same = bool(ms_comp.array[:len(comp_ref)].tobytes() == comp_ref.tobytes())
+                e2e_single = {"value": Lm * a.steps / dtm, "unit": UNIT, "h2d_bytes_per_step": int(N) * Lm,
+                              "d2h_bytes_per_step": Lm * (8 + comp_dtype.itemsize), "ms_per_step": dtm / a.steps * 1e3, "devices": m.count,
+                              "call": "sr_multi_run_streamed from ONE host process (rank 0): a context and a host thread per GPU inside the "
+                                      "library, contiguous column blocks, compact records land in place",
+                              "first_records_identical_to_per_process_run": same}
+                m.close()
+                for h in (ms_lnl, ms_comp) + ((ms_states,) if world > 1 else ()):
+                    h.free()
+            except Exception as exc:                        # never lose the main line over the extra leg
+                e2e_single = {"error": str(exc)}
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     clocks = sampler.stop()      # sampled over the resident AND the end-to-end timed regions
 
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (same launch size), else null
-    traffic = None
+    traffic, traffic_note = None, None
     try:
-        if (a.taxa, a.columns, a.ncat, a.model) == (1000, 1_000_000, 4, "wag"):
-            prof_json = json.load(open(os.path.join(ROOT, "profiles", "r01_prune_kernel_clade_tables_ncu_full_1Mcols.json")))
+        if a.config == 3 and L == 1_000_000 and not a.distinct:
+            prof_json = json.load(open(os.path.join(ROOT, "profiles", "r02_prune_kernel_ncu_full_1Mcols.json")))
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-            traffic = sum(float(prof_json[k]["value"]) * scale[prof_json[k]["unit"]]
-                          for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            traffic = sum(float(prof_json[k]["value"]) * scale[prof_json[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            traffic_note = ("bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of prune_kernel from "
+                            "profiles/r02_prune_kernel_ncu_full_1Mcols.json (same launch size)")
     except Exception:
         traffic = None
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(a),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic" if c.get("kind") != "example" else "reference example files",
+            "config": workload_config(a, c, L, world),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": traffic,
-                         "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of prune_kernel from "
-                                         "profiles/r01_prune_kernel_clade_tables_ncu_full_1Mcols.json; the kernel's own HBM need is "
-                                         "K*N bytes of states in + K*328 bytes of root partials out per column = 5.3 GB per launch, plus "
-                                         "the rows of the clade tables that miss L2 (0.8 GB measured; L2 hit rate 92 %) "
-                                         "(0.9 % of the HBM roof: the path is FP64-tensor-bound, not HBM-bound)",
+                         "frac": achieved / peak_tflops, "traffic": traffic, "traffic_note": traffic_note,
                          "kernel": "prune_kernel (FP64 DMMA m8n8k4)", "kernel_ms": k2_ms,
                          "kernel_share_of_step": prof["ms_prune"] / ms if world == 1 else None,
                          "flops_per_column": flops_per_col,
@@ -350,12 +510,13 @@ def run_b200(a):
                                           "flops of SURVEY 8d, `executed`/`frac_executed` only the flops prune_kernel still performs "
                                           "per column (its tensor-pipe efficiency; ceiling 0.83 from the 20->24 padding)",
                          "peak_source": "live DMMA probe (sr_measure_fp64_peak) on this GPU; MEASURED_PEAKS.json has no FP64 entry; "
-                                        "nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s"},
-            "e2e": e2e, "e2e_compact": e2e_compact, "numa_node": numa_node, "gpu_launches": launches,
-            "kernel_ms": {"pbuild_and_clade_tables_per_step": prof["ms_pbuild"] / max(1, a.steps), "prune": k2_ms,
+                                        "nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s; cuBLAS DGEMM beside it: profiles/fp64_peak_r02.json"},
+            "e2e": e2e, "e2e_full_joint": e2e_full, "e2e_single_process": e2e_single, "numa_node": numa_node, "gpu_launches": launches,
+            "kernel_ms": {"pbuild_and_clade_tables_per_step": prof["ms_pbuild"] / max(1, a.steps),
+                          "clade_index": prof["ms_index"] / max(1, prof["n_index"]), "prune": k2_ms,
                           "root": prof["ms_root"] / max(1, prof["n_root"])},
             "clocks": clocks, "total_lnl": total_lnl,
-            "schedule": {"steps": info["n_steps"], "stack_depth": info["stack_depth"]}}
+            "schedule": {"steps": info["n_steps"], "stack_depth": info["stack_depth"], "cherries": n_cherry, "pitchforks": n_fork}}
 
     # ---- cpu_baseline: the reference's CPU algorithm on this box's host cores (rank 0, N=1 only)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -365,8 +526,8 @@ def run_b200(a):
         res = {}
         for mode, key, tgt in ((2, "A_jar_faithful", a.cpu_seconds), (1, "B_p_rebuild_only", a.cpu_seconds / 3),
                                (0, "C_hoisted_honest_cpu", a.cpu_seconds / 3)):
-            n = calibrate_cpu_sample(a, threads, mode, flat, rates, base, tgt)
-            dt = cpu_reference_run(a, n, threads, mode, flat, a.model, rates, base)
+            n = calibrate_cpu_sample(threads, mode, flat, model, c["model"], rates, base, tgt)
+            dt = cpu_reference_run(n, threads, mode, flat, model, c["model"], rates, base)
             res[key] = {"columns_per_s": n / dt, "sample_columns": n, "seconds": dt}
         line["cpu_baseline"] = {
             "value": res["A_jar_faithful"]["columns_per_s"], "unit": UNIT, "cores": threads, "kind": "port",

@@ -76,6 +76,7 @@ typedef struct {
     double  ms_root;    int64_t n_root;         /* K3: root-branch joint / marginal   */
     int64_t columns_pruned;                     /* columns processed by K2 launches   */
     int64_t columns_in, columns_unique;         /* "compress_patterns": columns seen / distinct patterns computed */
+    double  ms_index;   int64_t n_index;        /* K0b: clade-index pre-pass (one launch per K2 launch when the tree has clade tables) */
 } sr_profile;
 
 /* Replaces: `Executors.newFixedThreadPool(nThreads)` (SubRecon.java:109) — the worker pool becomes a GPU. */

@@ -637,7 +637,9 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
         // K0b: one table-row index per (clade gather, column). The rows are padded past the launch's last column (the
         // alignment block's pitch leaves >= 256 bytes of slack, filled with the missing-data code).
         const unsigned by = (unsigned)std::min<int64_t>((ncp / 2 + 255) / 256, 4096);
+        prof_begin(c, s, 3, n);
         clade_index_kernel<<<dim3((unsigned)n_cg, by), 256, 0, s>>>(d_states, pitch, col_start, c->d_cgathers.as<int4>(), ncp, c->d_cidx.as<uint16_t>());
+        prof_end(c, s);
         CUDA_TRY(c, cudaGetLastError());
     }
     PruneParams p{};
@@ -1243,6 +1245,7 @@ static int sr_get_profile_impl(sr_ctx* c, sr_profile* out) {
         if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
             if (e.kind == 0) { c->prof.ms_pbuild += ms; ++c->prof.n_pbuild; }
             else if (e.kind == 1) { c->prof.ms_prune += ms; ++c->prof.n_prune; c->prof.columns_pruned += e.cols; }
+            else if (e.kind == 3) { c->prof.ms_index += ms; ++c->prof.n_index; }
             else { c->prof.ms_root += ms; ++c->prof.n_root; }
         } else {
             cudaGetLastError();

@@ -66,7 +66,8 @@ class Profile(ctypes.Structure):
     _fields_ = [("ms_pbuild", ctypes.c_double), ("n_pbuild", ctypes.c_int64),
                 ("ms_prune", ctypes.c_double), ("n_prune", ctypes.c_int64),
                 ("ms_root", ctypes.c_double), ("n_root", ctypes.c_int64),
-                ("columns_pruned", ctypes.c_int64), ("columns_in", ctypes.c_int64), ("columns_unique", ctypes.c_int64)]
+                ("columns_pruned", ctypes.c_int64), ("columns_in", ctypes.c_int64), ("columns_unique", ctypes.c_int64),
+                ("ms_index", ctypes.c_double), ("n_index", ctypes.c_int64)]
 
 
 def build(force=False):

@@ -105,6 +105,24 @@ class SiteResult:
             self._sort_by_prob()
         return self
 
+    @classmethod
+    def from_compact_like_java(cls, site, rec, threshold, sort_by_prob=True, sig_digits=DEFAULT_SIG_DIGITS):
+        """What the Java host does with a compact record (java/subrecon/recon/NativeRecon.java::reconstruct): SiteResult only
+        has the matrix constructor, so the kept entries are put back into an otherwise empty 20x20 matrix, plus carriers for
+        maxIIProb / maxProb when those are below the threshold, and the reference's own scan runs on it."""
+        n, cap = int(rec["n_kept"]), len(rec["pair"])
+        if n > cap:
+            raise ValueError(f"compact record overflow: {n} entries kept, capacity {cap}")
+        m = np.zeros(400)
+        for i in range(n):
+            m[int(rec["pair"][i])] = float(rec["prob"][i])
+        max_ii, max_p = float(rec["max_ii_prob"]), float(rec["max_prob"])
+        if max_ii < threshold:
+            m[0] = max(m[0], max_ii)
+        if max_p < threshold and max_p > max_ii:
+            m[1] = max(m[1], max_p)
+        return cls(site, float(rec["lnl"]), m, threshold, sort_by_prob, sig_digits)
+
     def _sort_by_prob(self):                                           # :96-108, stable descending bubble sort
         pr, sb = self.probs, self.subs
         for i in range(len(pr) - 1):

@@ -534,18 +534,143 @@ def test_compact_matches_site_result_scan(ctx, example_problem):
     p = example_problem
     setup(ctx, p)
     full = ctx.run()
-    for thr in (0.5, 0.2, 0.0):
-        c = ctx.run(want_joint=False, want_compact=True, threshold=thr)["compact"]
-        for i in range(len(c)):
-            J = full["joint"][i]
-            sr = recon.SiteResult(i, full["lnl"][i], J, thr, sort_by_prob=False)
-            assert c["max_prob"][i] == sr.get_max_prob() and c["max_ii_prob"][i] == sr.get_max_ii_prob()
-            assert c["n_kept"][i] == len(sr.probs)
-            assert bool(c["interesting"][i]) == (sr.get_max_ii_prob() <= 1.0 - thr and sr.get_max_prob() >= thr)
-            k = min(len(sr.probs), 8)
-            assert c["prob"][i][:k].tolist() == sr.probs[:k]
-            if len(sr.probs) <= 8:
+    try:
+        for thr in (0.5, 0.2, 0.0):
+            cap = native.compact_cap_for(thr)
+            ctx.set_option("compact_cap", cap)
+            c = ctx.run(want_joint=False, want_compact=True, threshold=thr)["compact"]
+            for i in range(len(c)):
+                J = full["joint"][i]
+                sr = recon.SiteResult(i, full["lnl"][i], J, thr, sort_by_prob=False)
+                assert c["max_prob"][i] == sr.get_max_prob() and c["max_ii_prob"][i] == sr.get_max_ii_prob()
+                assert c["n_kept"][i] == len(sr.probs) <= cap
+                assert bool(c["interesting"][i]) == (sr.get_max_ii_prob() <= 1.0 - thr and sr.get_max_prob() >= thr)
+                assert c["prob"][i][:len(sr.probs)].tolist() == sr.probs
                 assert str(recon.SiteResult.from_compact(i, c[i])) == str(recon.SiteResult(i, full["lnl"][i], J, thr))
+    finally:
+        ctx.set_option("compact_cap", 8)
+
+
+def test_compact_capacity_is_lossless_or_refused(ctx, example_problem):
+    """A compact record holds `compact_cap` entries (default 8). A threshold that could keep more (floor(1/t) > cap) is
+    refused instead of truncated; with the capacity raised to sr_compact_cap_for(t) every kept entry is there."""
+    p = example_problem
+    setup(ctx, p)
+    full = ctx.run()
+    assert [native.compact_cap_for(t) for t in (0.5, 0.34, 0.2, 0.125, 0.1, 0.01, 0.0)] == [2, 2, 5, 8, 10, 100, 400]
+    with pytest.raises(native.SrError, match="compact_cap"):
+        ctx.run(want_joint=False, want_compact=True, threshold=0.1)
+    with pytest.raises(native.SrError, match="compact_cap"):
+        ctx.run_streamed(p.states, want_joint=False, want_compact=True, threshold=0.0)
+    try:
+        for thr in (0.5, 0.1, 0.03, 0.0):
+            cap = native.compact_cap_for(thr)
+            ctx.set_option("compact_cap", cap)
+            assert native.compact_dtype(cap).itemsize == native.lib().sr_compact_stride(cap)
+            for runner in (lambda: ctx.run(want_joint=False, want_compact=True, threshold=thr),
+                           lambda: ctx.run_streamed(p.states, want_joint=False, want_compact=True, threshold=thr)):
+                c = runner()["compact"]
+                assert c.dtype.itemsize == native.compact_dtype(cap).itemsize and np.array_equal(c["lnl"], full["lnl"])
+                for i in range(len(c)):
+                    sr = recon.SiteResult(i, full["lnl"][i], full["joint"][i], thr, sort_by_prob=False)
+                    assert c["n_kept"][i] == len(sr.probs) <= cap
+                    assert c["prob"][i][:len(sr.probs)].tolist() == sr.probs
+                    assert [recon.AA_ORDER[a // 20] + recon.AA_ORDER[a % 20] for a in c["pair"][i][:len(sr.probs)]] == sr.subs
+                    assert np.all(c["pair"][i][len(sr.probs):] == -1) and np.all(c["prob"][i][len(sr.probs):] == 0.0)
+    finally:
+        ctx.set_option("compact_cap", 8)
+    with pytest.raises(native.SrError):
+        ctx.set_option("compact_cap", 401)
+
+
+@pytest.mark.parametrize("cfg,n", [(1, 130), (2, 10_000), (3, 4096)])
+def test_printed_output_via_compact_equals_via_full_joint(ctx, example_problem, cfg, n):
+    """The Java host builds its SiteResults from compact records (java/subrecon/recon/NativeRecon.java); what it prints
+    must be what the 400-probability route prints — thresholds 0.5 (default), 0.2, 0.125, sorted and -nosort, -verbose."""
+    p = example_problem if cfg == 1 else synthetic(cfg, n)
+    setup(ctx, p)
+    full = ctx.run()
+    try:
+        for thr in (0.5, 0.2, 0.125):
+            ctx.set_option("compact_cap", native.compact_cap_for(thr))
+            c = ctx.run(want_joint=False, want_compact=True, threshold=thr)["compact"]
+            for sort in (True, False):
+                a = [recon.SiteResult(i, full["lnl"][i], full["joint"][i], thr, sort) for i in range(n)]
+                b = [recon.SiteResult.from_compact_like_java(i, c[i], thr, sort) for i in range(n)]
+                d = [recon.SiteResult.from_compact(i, c[i], sort) for i in range(n)]
+                for verbose in (False, True):
+                    want = recon.run_columns(a, verbose, thr)
+                    assert recon.run_columns(b, verbose, thr) == want and recon.run_columns(d, verbose, thr) == want
+                assert [x.get_max_prob() for x in b] == [x.get_max_prob() for x in a]
+                assert [x.get_max_ii_prob() for x in b] == [x.get_max_ii_prob() for x in a]
+            assert np.array_equal(c["interesting"] != 0, [x.get_max_ii_prob() <= 1.0 - thr and x.get_max_prob() >= thr for x in a])
+    finally:
+        ctx.set_option("compact_cap", 8)
+
+
+def test_multi_device_entry(ctx, example_problem):
+    """sr_multi_*: one host process, one context + one host thread per device, contiguous column blocks, results in place.
+    On a one-GPU box the "devices" are three contexts on cuda:0; with more GPUs every visible device takes part."""
+    import torch
+    p = example_problem
+    setup(ctx, p)
+    ref = ctx.run()
+    big = np.tile(p.states, (1, 37))[:, :4801]                                # odd size: ragged last block
+    devices = list(range(torch.cuda.device_count())) if torch.cuda.device_count() > 1 else [0, 0, 0]
+    m = native.MultiContext(devices)
+    try:
+        assert m.count == len(devices)
+        m.set_model(p.model.Eval, p.model.Evec, p.model.Ievc, p.model.pi)
+        m.set_rates(p.rates)
+        m.set_tree(p.flat)
+        pin = native.PinnedArray(big.shape, np.uint8)
+        pin.array[:] = big
+        for src in (big, pin.array):
+            r = m.run_streamed(src, want_joint=True, want_compact=True)
+            assert np.array_equal(r["lnl"], np.tile(ref["lnl"], 37)[:4801])
+            assert np.array_equal(r["joint"], np.tile(ref["joint"], (37, 1, 1))[:4801])
+            assert np.array_equal(r["compact"]["lnl"], r["lnl"])
+        part = m.run_streamed(pin.array, site0=77, n=1000, want_joint=False, want_compact=True)
+        assert np.array_equal(part["lnl"], r["lnl"][77:1077]) and part["compact"].tobytes() == r["compact"][77:1077].tobytes()
+        one = m.run_streamed(pin.array, site0=4800, n=1)                       # -site n: one column, most devices idle
+        assert np.array_equal(one["lnl"], r["lnl"][4800:])
+        m.set_option("compact_cap", 2)
+        r2 = m.run_streamed(pin.array, want_joint=False, want_compact=True, threshold=0.5)
+        assert r2["compact"].dtype.itemsize == 56 and np.array_equal(r2["compact"]["prob"], r["compact"]["prob"][:, :2])
+        with pytest.raises(native.SrError, match="device .*compact_cap"):
+            m.run_streamed(pin.array, want_joint=False, want_compact=True, threshold=0.2)
+        with pytest.raises(native.SrError, match="unknown option"):
+            m.set_option("no_such_option", 1)
+        pin.free()
+    finally:
+        m.close()
+    with pytest.raises(native.SrError):
+        native.MultiContext([0, 99])
+
+
+def test_strict_root_option(ctx):
+    """a tip as root child with K > 1 makes the reference throw on every column (utils/Utils.java:56-70).
+    With "strict_root" the input is rejected once, from whichever of sr_set_tree / sr_set_rates completes the combination."""
+    flat = treeio.flatten_tree(treeio.parse_newick("(a:0.1,(b:0.2,c:0.3):0.1);"))
+    ok = treeio.flatten_tree(treeio.parse_newick("((a:0.1,d:0.1):0.1,(b:0.2,c:0.3):0.1);"))
+    model = oracle.OracleModel("WAG")
+    c = native.Context(0)
+    try:
+        c.set_option("strict_root", 1)
+        c.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
+        c.set_rates(oracle.gamma_rates(4, 0.5))
+        with pytest.raises(native.SrError, match="child of the root is a tip") as ei:
+            c.set_tree(flat)
+        assert ei.value.code == -5
+        c.set_tree(ok)
+        c.set_rates(np.array([1.0]))
+        c.set_tree(flat)                                                   # K = 1: the reference handles it
+        with pytest.raises(native.SrError, match="child of the root is a tip"):
+            c.set_rates(oracle.gamma_rates(2, 0.5))
+        c.set_alignment(treeio.encode_alignment(["A-", "AR", "RR"]))
+        assert np.isfinite(c.run()["lnl"]).all()                           # still K = 1
+    finally:
+        c.close()
 
 
 def test_host_mirror_interface(ctx, example_problem):
