@@ -126,3 +126,23 @@ def simulate_alignment(tree: Tree, model, rates, n_sites: int, seed: int, gap_fr
         r = rng.random(out.shape)
         out[r < gap_frac + x_frac] = MISSING
     return out
+
+
+def _sim_job(job):
+    tree, model, rates, n, seed = job
+    return simulate_alignment(tree, model, rates, n, seed)
+
+
+def simulate_alignment_parallel(tree: Tree, model, rates, n_sites: int, seed: int, block=16384, procs=None) -> np.ndarray:
+    """`n_sites` DISTINCT simulated columns: blocks of `block` columns, each with its own seed, spread over the host cores."""
+    import multiprocessing as mp
+    import os
+    starts = list(range(0, n_sites, block))
+    jobs = [(tree, model, rates, min(block, n_sites - c0), seed + 7919 * (i + 1)) for i, c0 in enumerate(starts)]
+    procs = procs or max(1, min(len(jobs), os.cpu_count() or 1))
+    if procs == 1 or len(jobs) == 1:
+        parts = [_sim_job(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            parts = pool.map(_sim_job, jobs)
+    return np.concatenate(parts, axis=1)

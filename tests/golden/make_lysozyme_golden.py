@@ -70,11 +70,15 @@ def main():
             cache[t] = P
         return cache[t]
 
-    AA = treeio.AA_ORDER
+    # the reference's own tip lookup, executed from the jar (molevo/AdvancedAlignmentAminoAcid.java:34-40)
+    aa_type = vm.call("pal/datatype/DataTypeTool", "getUniverisalAminoAcids", "()Lpal/datatype/MolecularDataType;")
+    state_cache = {}
 
     def state_of(name, site):
-        c = seqs[row[name]][site].upper()
-        return AA.index(c) if c in AA else 20
+        c = seqs[row[name]][site]
+        if c not in state_cache:
+            state_cache[c] = vm.call(aa_type, "getState", "(C)I", ord(c))
+        return state_cache[c]
 
     def down(v, site, count, rate):
         cond = [0.0] * 20

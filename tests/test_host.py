@@ -1,4 +1,7 @@
 """Host logic either side of the path: readers, flatteners, SiteResult formatting (no GPU)."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -113,3 +116,29 @@ def test_cli_frequency_normalisation():
         palmodel.normalise_cli_frequencies([0.5, 0.5])
     with pytest.raises(ValueError, match="not recognised"):
         palmodel.host_model("lg")
+
+
+def jar_state_lut():
+    """The reference's tip-state lookup for every byte, from the golden made by executing pal.jar (tests/golden/make_states_golden.py)."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aa_states_golden.json")))
+    return np.array([s if 0 <= s < 20 else treeio.MISSING for s in g["states"]], dtype=np.uint8), g["states"]
+
+
+def test_state_lut_is_what_the_jar_computes():
+    """`DataTypeTool.getUniverisalAminoAcids().getState(c)` (molevo/AdvancedAlignmentAminoAcid.java:34-40), executed from
+    PAL's bytecode for c = 0..255, against the host's encode table (and through it the device's, tests/test_gpu_parity.py::
+    test_residue_letters_encoded_on_device). The jar answers 20 (unknown), 21 ('*') and -2 (gap) for non-residues: all of
+    them fail `0 <= state < 20` in JointBranchReconstruction.java:199-205 and become missing data."""
+    lut, raw = jar_state_lut()
+    assert np.array_equal(lut, treeio._STATE_LUT)
+    assert sorted(set(raw)) == [-2] + list(range(22)) and raw[ord("-")] == -2 and raw[ord("*")] == 21 and raw[ord("X")] == 20
+    assert [raw[ord(c)] for c in treeio.AA_ORDER] == list(range(20)) == [raw[ord(c.lower())] for c in treeio.AA_ORDER]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/lib/pal.jar"), reason="reference jar only in the build container")
+def test_state_golden_regenerates_from_the_jar():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_states_golden
+    cls, states, stubbed = make_states_golden.jar_states()
+    assert cls == "pal/datatype/SpecificAminoAcids" and stubbed == [] and states == jar_state_lut()[1]

@@ -20,19 +20,26 @@ ap.add_argument("--taxa", type=int, default=1000)
 ap.add_argument("--tree", default="yule")
 ap.add_argument("--ncat", type=int, default=4)
 ap.add_argument("--uniform", action="store_true", help="uniform random states instead of simulated columns")
+ap.add_argument("--distinct", action="store_true", help="simulate every column down the tree (host cores in parallel) instead of tiling 4096")
+ap.add_argument("--model", default="wag")
 ap.add_argument("--const", action="store_true", help="every tip in state 0 (no shared-memory bank conflicts in the tip gathers)")
 a = ap.parse_args()
 
 tree = {"yule": synth.yule_tree, "balanced": synth.balanced_tree, "caterpillar": synth.caterpillar_tree}[a.tree](a.taxa, seed=3)
-model = palmodel.host_model("wag")
+model = palmodel.host_model(a.model)
 rates = palmodel.gamma_rates(a.ncat, 0.5)
 if a.const:
     base = np.zeros((a.taxa, 4096), dtype=np.uint8)
 elif a.uniform:
     base = np.random.default_rng(1).integers(0, 20, size=(a.taxa, 4096), dtype=np.uint8)
+elif a.distinct:
+    base = None
 else:
     base = synth.simulate_alignment(tree, model, rates, 4096, seed=103)
-states = np.tile(base, (1, (a.cols + 4095) // 4096))[:, :a.cols]
+if base is None:
+    states = synth.simulate_alignment_parallel(tree, model, rates, a.cols, seed=103)
+else:
+    states = np.tile(base, (1, (a.cols + 4095) // 4096))[:, :a.cols]
 ctx = native.Context(0)
 if a.rescale:
     ctx.set_option("rescale_every", a.rescale)
@@ -52,5 +59,5 @@ for _ in range(a.reps):
 p = ctx.profile(reset=True)
 ms = p["ms_prune"] / p["n_prune"]
 tf = info["flops_per_column_rate"] * len(rates) * a.cols / ms * 1e-9
-print(f"tree={a.tree} taxa={a.taxa} cols={a.cols} tables={a.tables} k_fastest={a.k_fastest} K={a.ncat} depth={info['stack_depth']} steps={info['n_steps']}: "
+print(f"tree={a.tree} taxa={a.taxa} cols={a.cols} distinct={int(a.distinct)} tables={a.tables} k_fastest={a.k_fastest} K={a.ncat} depth={info['stack_depth']} steps={info['n_steps']}: "
       f"prune {ms:.3f} ms/launch  {a.cols / ms * 1e-3:.3f} Mcol/s  {tf:.2f} TFLOP/s  root {p['ms_root'] / p['n_root']:.3f} ms")
