@@ -167,34 +167,68 @@ def fill_states(a, c, dst, base, rank, world):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """SM clock, power and clock-event (throttle) reasons of this rank's GPU while the timed regions run. Read in-process
+    through NVML (the same source `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons...` reads — B200_PROFILING.md's
+    clocks line): spawning nvidia-smi five times a second per rank makes eight of them queue on the driver at N=8 and stalls
+    the ranks' own kernel launches, which is what a benchmark must not do to itself. Falls back to nvidia-smi when NVML
+    cannot be loaded. Samples carry a time stamp so that a leg's own window can be reported (`window`)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, bus_id=None, period=0.1):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_ev = index, [], threading.Event()
+        self.index, self.samples, self._stop_ev, self.period = index, [], threading.Event(), period
+        self.nvml, self.handle, self.max_mhz = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode()) if bus_id else pynvml.nvmlDeviceGetHandleByIndex(index)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.masks = [pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                          pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap]
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            watts = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+            bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            return sm, self.max_mhz, watts, [bool(bits & m) for m in self.masks]
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        return float(f[0]), float(f[1]), float(f[2]), [x.lower() == "active" for x in f[3:7]]
 
     def run(self):
         while not self._stop_ev.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.samples.append((time.perf_counter(),) + self._sample())
             except Exception:
                 pass
-            self._stop_ev.wait(0.2)
+            self._stop_ev.wait(self.period if self.nvml is not None else 0.5)
 
     def stop(self):
         self._stop_ev.set()
         self.join(timeout=6)
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 7 and s[3 + i].lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return self.window(None, None)
+
+    def window(self, t0, t1):
+        """Statistics over the samples taken in [t0, t1] (perf_counter times; None = everything)."""
+        ss = [x for x in self.samples if (t0 is None or x[0] >= t0) and (t1 is None or x[0] <= t1)]
+        if not ss and self.samples and t0 is not None:          # a region shorter than the sampling period: nearest sample
+            ss = [min(self.samples, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))]
+        sm = [x[1] for x in ss]
+        reasons = sorted({self.NAMES[i] for x in ss for i in range(4) if x[4][i]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max((x[2] for x in ss), default=None), "power_w_max": max((x[3] for x in ss), default=None),
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def bind_to_gpu_numa_node(local):
@@ -348,16 +382,21 @@ def run_b200(a):
     peak_tflops = ctx.measure_fp64_peak(150.0)
     ctx.set_option("profile", 1)
     ctx.profile(reset=True)
-    sampler = ClockSampler(local)
-    barrier()
+    props = torch.cuda.get_device_properties(local)
+    bus_id = "%08x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), getattr(props, "pci_bus_id", 0), getattr(props, "pci_device_id", 0))
+    sampler = ClockSampler(local, bus_id if hasattr(props, "pci_bus_id") else None)
     sampler.start()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_res0 = time.perf_counter()
     ev0.record(tstream)
     for _ in range(a.steps):
         step_resident()
     ev1.record(tstream)
     barrier()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    t_res1 = time.perf_counter()
+    ms_rank = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(ms_rank)
     prof = ctx.profile(reset=True)
     ctx.set_option("profile", 0)
     value = total_columns * a.steps / (ms * 1e-3)
@@ -480,7 +519,20 @@ def run_b200(a):
         if world > 1:
             dist.barrier(group=cpu_group)
 
-    clocks = sampler.stop()      # sampled over the resident AND the end-to-end timed regions
+    clocks_all = sampler.stop()                      # every leg (resident and end-to-end)
+    clocks = sampler.window(t_res0, t_res1)          # the region `value` was timed over
+    clocks["whole_run"] = {k: clocks_all[k] for k in ("sm_mhz", "sm_min_mhz", "power_w_max", "reasons", "samples")}
+    # every rank's own view of the resident region: step time, kernel time, clocks, power (the reported time is their max)
+    mine = {"rank": rank, "ms_per_step": ms_rank / a.steps, "prune_ms": prof["ms_prune"] / max(1, prof["n_prune"]),
+            "sm_mhz": clocks["sm_mhz"], "sm_min_mhz": clocks["sm_min_mhz"], "power_w_max": clocks["power_w_max"], "reasons": clocks["reasons"]}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine, group=cpu_group)
+        reasons_any = sorted({r for x in per_rank for r in x["reasons"]})
+        clocks["reasons"] = reasons_any             # any rank's throttle reason counts for the run
+        clocks["sm_mhz"] = float(np.median([x["sm_mhz"] for x in per_rank if x["sm_mhz"] is not None]))
+        clocks["sm_min_mhz"] = min(x["sm_min_mhz"] for x in per_rank if x["sm_min_mhz"] is not None)
 
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (same launch size), else null
     traffic, traffic_note = None, None
@@ -515,7 +567,7 @@ def run_b200(a):
             "kernel_ms": {"pbuild_and_clade_tables_per_step": prof["ms_pbuild"] / max(1, a.steps),
                           "clade_index": prof["ms_index"] / max(1, prof["n_index"]), "prune": k2_ms,
                           "root": prof["ms_root"] / max(1, prof["n_root"])},
-            "clocks": clocks, "total_lnl": total_lnl,
+            "clocks": clocks, "per_rank": per_rank, "total_lnl": total_lnl,
             "schedule": {"steps": info["n_steps"], "stack_depth": info["stack_depth"], "cherries": n_cherry, "pitchforks": n_fork}}
 
     # ---- cpu_baseline: the reference's CPU algorithm on this box's host cores (rank 0, N=1 only)

@@ -116,6 +116,12 @@ struct sr_ctx {
     // pinned bounce buffers for pageable caller memory
     void* h_bounce[3] = {nullptr, nullptr, nullptr};
     size_t h_bounce_cap[3] = {0, 0, 0};
+    // page-locked staging for the small per-rebuild uploads of ensure_pstream (model, rates, records, slots): copies from
+    // it are truly asynchronous, so rebuilding the matrices never drains the stream; ev_stage marks the last copy out of it
+    void* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    cudaEvent_t ev_stage = nullptr;
+    bool stage_busy = false;
 
     std::vector<EvPair> events;
     sr_profile prof{};
@@ -534,20 +540,53 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     CUDA_TRY(c, c->d_slotblen.reserve(sizeof(double) * n_slots));
     CUDA_TRY(c, c->d_pstream.reserve(sizeof(double) * (size_t)c->K * c->rate_stride));
     CUDA_TRY(c, c->d_proot.reserve(sizeof(double) * (size_t)c->K * 400));
+    // Every upload goes through ONE page-locked staging buffer and is enqueued on the SAME stream as the kernels that read
+    // it (the context's streams are non-blocking: a plain cudaMemcpy on the legacy stream is not ordered against them, and
+    // a copy from pageable memory may return before the DMA has landed). Nothing here waits for the GPU: the only host-side
+    // wait is for the previous rebuild's copies to have left the staging buffer, which happened long ago.
+    const int n_cherry = (int)c->cherry_node.size();
+    struct Piece { void* dst; const void* src; size_t bytes; };
     double hm[840];
     memcpy(hm, c->eval, 160); memcpy(hm + 20, c->evec, 3200); memcpy(hm + 420, c->ievc, 3200); memcpy(hm + 820, c->pi, 160);
-    // Copies are enqueued on the SAME stream as the kernels that read them (the context's streams are
-    // non-blocking: a plain cudaMemcpy on the legacy stream is not ordered against them, and from pageable memory
-    // it may return before the DMA has landed). The stream is drained before the staging arrays go out of scope.
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_model.p, hm, sizeof(hm), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_rates.p, c->rates.data(), sizeof(double) * c->K, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_crec.p, c->crec.data(), sizeof(uint32_t) * 4 * n_steps, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_prec.p, c->prec.data(), sizeof(uint32_t) * 8 * n_steps, cudaMemcpyHostToDevice, s));
-    if (n_cg) CUDA_TRY(c, cudaMemcpyAsync(c->d_cgathers.p, c->clade_gathers.data(), sizeof(int32_t) * 4 * n_cg, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_slotkind.p, c->slot_kind.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_slotoff.p, c->slot_off.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_slotblen.p, c->slot_blen.data(), sizeof(double) * n_slots, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (n_cherry > 0) {
+        CUDA_TRY(c, c->d_ctab.reserve(sizeof(double) * (size_t)c->K * c->ctab_rows * CHERRY_ROW_DOUBLES));
+        CUDA_TRY(c, c->d_cherry_blen.reserve(sizeof(double) * 5 * n_cherry));
+        CUDA_TRY(c, c->d_cherry_meta.reserve((sizeof(int64_t) + sizeof(int32_t)) * (size_t)n_cherry + 16));
+    }
+    int64_t* d_rowoff = c->d_cherry_meta.as<int64_t>();
+    int32_t* d_kind = reinterpret_cast<int32_t*>(d_rowoff + n_cherry);
+    const Piece pieces[] = {
+        {c->d_model.p, hm, sizeof(hm)},
+        {c->d_rates.p, c->rates.data(), sizeof(double) * c->K},
+        {c->d_crec.p, c->crec.data(), sizeof(uint32_t) * 4 * n_steps},
+        {c->d_prec.p, c->prec.data(), sizeof(uint32_t) * 8 * n_steps},
+        {c->d_cgathers.p, c->clade_gathers.data(), sizeof(int32_t) * 4 * n_cg},
+        {c->d_slotkind.p, c->slot_kind.data(), sizeof(int32_t) * n_slots},
+        {c->d_slotoff.p, c->slot_off.data(), sizeof(int32_t) * n_slots},
+        {c->d_slotblen.p, c->slot_blen.data(), sizeof(double) * n_slots},
+        {c->d_cherry_blen.p, c->cherry_blen.data(), sizeof(double) * 5 * n_cherry},
+        {d_rowoff, c->cherry_rowoff.data(), sizeof(int64_t) * n_cherry},
+        {d_kind, c->cherry_kind.data(), sizeof(int32_t) * n_cherry},
+    };
+    size_t total = 0;
+    for (const Piece& pc : pieces) total += (pc.bytes + 15) & ~(size_t)15;
+    if (c->stage_busy) { CUDA_TRY(c, cudaEventSynchronize(c->ev_stage)); c->stage_busy = false; }
+    if (total > c->h_stage_cap) {
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr; c->h_stage_cap = 0;
+        CUDA_TRY(c, cudaHostAlloc(&c->h_stage, total + (total >> 2), cudaHostAllocPortable));
+        c->h_stage_cap = total + (total >> 2);
+    }
+    size_t off = 0;
+    for (const Piece& pc : pieces) {
+        if (pc.bytes) {
+            memcpy(static_cast<char*>(c->h_stage) + off, pc.src, pc.bytes);
+            CUDA_TRY(c, cudaMemcpyAsync(pc.dst, static_cast<char*>(c->h_stage) + off, pc.bytes, cudaMemcpyHostToDevice, s));
+        }
+        off += (pc.bytes + 15) & ~(size_t)15;
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev_stage, s));
+    c->stage_busy = true;
     PBuildParams pp{};
     pp.eval = c->d_model.as<double>();
     pp.evec = pp.eval + 20;
@@ -566,17 +605,8 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
     pbuild_kernel<<<dim3(n_slots + 1, c->K), 128, 0, s>>>(pp);
     prof_end(c, s);
     CUDA_TRY(c, cudaGetLastError());
-    const int n_cherry = (int)c->cherry_node.size();
     if (n_cherry > 0) {
         const int64_t stride = c->ctab_rows * CHERRY_ROW_DOUBLES;
-        CUDA_TRY(c, c->d_ctab.reserve(sizeof(double) * (size_t)c->K * stride));
-        CUDA_TRY(c, c->d_cherry_blen.reserve(sizeof(double) * 5 * n_cherry));
-        CUDA_TRY(c, c->d_cherry_meta.reserve((sizeof(int64_t) + sizeof(int32_t)) * (size_t)n_cherry + 16));
-        int64_t* d_rowoff = c->d_cherry_meta.as<int64_t>();
-        int32_t* d_kind = reinterpret_cast<int32_t*>(d_rowoff + n_cherry);
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_cherry_blen.p, c->cherry_blen.data(), sizeof(double) * 5 * n_cherry, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(c, cudaMemcpyAsync(d_rowoff, c->cherry_rowoff.data(), sizeof(int64_t) * n_cherry, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(c, cudaMemcpyAsync(d_kind, c->cherry_kind.data(), sizeof(int32_t) * n_cherry, cudaMemcpyHostToDevice, s));
         CherryParams cp{};
         cp.eval = pp.eval; cp.evec = pp.evec; cp.ievc = pp.ievc; cp.rates = pp.rates;
         cp.blen = c->d_cherry_blen.as<double>();
@@ -590,7 +620,6 @@ int ensure_pstream(sr_ctx* c, cudaStream_t s) {
         cherry_kernel<<<dim3(n_cherry, c->K, 8), 256, usm, s>>>(cp);
         prof_end(c, s);
         CUDA_TRY(c, cudaGetLastError());
-        CUDA_TRY(c, cudaStreamSynchronize(s));       // the staging arrays are host memory owned by the context; keep it simple
     }
     c->p_dirty = false;
     return SR_OK;
@@ -825,11 +854,13 @@ static int sr_create_impl(sr_ctx** out, int device) {
             return fail(nullptr, SR_ERR_CUDA, "cannot create CUDA events");
         }
     }
+    if (cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
+        sr_destroy(c);
+        return fail(nullptr, SR_ERR_CUDA, "cannot create CUDA events");
+    }
     *out = c;
     return SR_OK;
 }
-
-
 
 static int sr_set_model_impl(sr_ctx* c, const double* eval, const double* evec, const double* ievc, const double* pi) {
     if (!c) return SR_ERR_ARG;
@@ -1570,6 +1601,8 @@ void sr_destroy(sr_ctx* c) {
     cudaDeviceSynchronize();
     for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int i = 0; i < 3; ++i) if (c->h_bounce[i]) cudaFreeHost(c->h_bounce[i]);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev_stage) cudaEventDestroy(c->ev_stage);
     for (int i = 0; i < 3; ++i) {
         if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
