@@ -421,15 +421,22 @@ struct CompactRec {            // must match sr_compact in include/subrecon_b200
 __host__ __device__ constexpr int compact_pairs_bytes(int cap) { return (2 * cap + 7) / 8 * 8; }
 __host__ __device__ constexpr int compact_stride(int cap) { return 32 + compact_pairs_bytes(cap) + 8 * cap; }
 
-// one warp per column; lane a < 20 owns row a of the 20x20 joint matrix
+// One warp per ROOT_COLS columns; lane a < 20 owns row a of each column's 20x20 joint matrix.
+// joint[a][b] ∝ Σ_k 2^(e_k-e_max) · π_a · A_k[a] · P_k^{tA+tB}[a][b] · B_k[b]: for every (k, b) a lane needs one entry of the
+// root-branch matrix (its own row: one conflict-free LDS) and B_k[b] of each column (a broadcast LDS). Shared-memory
+// wavefronts are what bound this kernel, so a warp works on ROOT_COLS = 2 columns at once: the matrix entry is loaded once
+// for both and the two B_k[b] sit side by side (one LDS.128 broadcast) — half the wavefronts per column. The arithmetic per
+// column is unchanged (same operations in the same order as with one column per warp).
 constexpr int ROOT_WARPS = 8;
+constexpr int ROOT_COLS = 2;
 // SMEMP: the K merged root-branch matrices are staged once per CTA in dynamic shared memory, transposed ([k][b][a]) so
 // that lane a's 20 reads per rate class are conflict-free; read straight from global memory they are 20 strided
 // 8-byte loads per lane and rate class, and the L1 sector traffic of those was what bounded this kernel.
 constexpr int ROOT_SMEM_MAX_K = 16;
 template <bool SMEMP>
-__global__ void __launch_bounds__(ROOT_WARPS * 32) root_kernel(RootParams p) {
-    __shared__ double sB[ROOT_WARPS][NS];
+__global__ void __launch_bounds__(ROOT_WARPS * 32, 2) root_kernel(RootParams p) {
+    constexpr int C = ROOT_COLS;
+    __shared__ __align__(16) double sB[ROOT_WARPS][NS][C];
     __shared__ double sOut[ROOT_WARPS][NS * NS];
     extern __shared__ __align__(16) double sP[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -441,88 +448,117 @@ __global__ void __launch_bounds__(ROOT_WARPS * 32) root_kernel(RootParams p) {
         }
         __syncthreads();
     }
-    for (int64_t oc = (int64_t)blockIdx.x * ROOT_WARPS + warp; oc < p.n; oc += (int64_t)gridDim.x * ROOT_WARPS) {
-        const int64_t col = oc + p.col_skip;
-        int emax = INT_MIN;
-        for (int k = 0; k < p.K; ++k) emax = max(emax, p.rootexp[(size_t)k * p.ncp + col]);
-        double row[NS];
+    const double pia = lane < NS ? p.pi[lane] : 0.0;
+    for (int64_t grp = (int64_t)blockIdx.x * ROOT_WARPS + warp; grp * C < p.n; grp += (int64_t)gridDim.x * ROOT_WARPS) {
+        const int64_t oc0 = grp * C;
+        const int ncol = (int)min((int64_t)C, p.n - oc0);
+        int64_t col[C];
+        int emax[C];
 #pragma unroll
-        for (int b = 0; b < NS; ++b) row[b] = 0.0;
-        const double pia = lane < NS ? p.pi[lane] : 0.0;
+        for (int c = 0; c < C; ++c) {
+            col[c] = oc0 + (c < ncol ? c : 0) + p.col_skip;              // a missing second column repeats the first (result unused)
+            emax[c] = INT_MIN;
+            for (int k = 0; k < p.K; ++k) emax[c] = max(emax[c], p.rootexp[(size_t)k * p.ncp + col[c]]);
+        }
+        double row[C][NS];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int b = 0; b < NS; ++b) row[c][b] = 0.0;
         for (int k = 0; k < p.K; ++k) {
-            const int e = p.rootexp[(size_t)k * p.ncp + col];
-            const double wk = ldexp(1.0, e - emax);                                     // exact, <= 1
-            const double* pa = p.rootpart + (((size_t)0 * p.K + k) * p.ncp + col) * NS;
-            const double* pb = p.rootpart + (((size_t)1 * p.K + k) * p.ncp + col) * NS;
+            double fa[C];
             __syncwarp();
-            if (lane < NS) sB[warp][lane] = pb[lane];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int e = p.rootexp[(size_t)k * p.ncp + col[c]];
+                const double wk = ldexp(1.0, e - emax[c]);                               // exact, <= 1
+                const double* pa = p.rootpart + (((size_t)0 * p.K + k) * p.ncp + col[c]) * NS;
+                const double* pb = p.rootpart + (((size_t)1 * p.K + k) * p.ncp + col[c]) * NS;
+                if (lane < NS) {
+                    sB[warp][lane][c] = pb[lane];
+                    fa[c] = wk * (pia * pa[lane]);
+                }
+            }
             __syncwarp();
             if (lane < NS) {
-                const double fa = wk * (pia * pa[lane]);
                 if (SMEMP) {
                     const double* pr = sP + k * (NS * NS) + lane;
 #pragma unroll
-                    for (int b = 0; b < NS; ++b) row[b] = fma(fa * pr[b * NS], sB[warp][b], row[b]);
+                    for (int b = 0; b < NS; ++b) {
+                        const double prb = pr[b * NS];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) row[c][b] = fma(fa[c] * prb, sB[warp][b][c], row[c][b]);
+                    }
                 } else {
                     const double* pr = p.proot + (size_t)k * NS * NS + lane * NS;
 #pragma unroll
-                    for (int b = 0; b < NS; ++b) row[b] = fma(fa * pr[b], sB[warp][b], row[b]);
+                    for (int b = 0; b < NS; ++b) {
+                        const double prb = pr[b];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) row[c][b] = fma(fa[c] * prb, sB[warp][b][c], row[c][b]);
+                    }
                 }
             }
         }
-        double rs = 0.0;
 #pragma unroll
-        for (int b = 0; b < NS; ++b) rs += row[b];
-        double tot = rs;
+        for (int c = 0; c < C; ++c) {
+            if (c >= ncol) break;
+            const int64_t oc = oc0 + c;
+            double rs = 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        const double inv = 1.0 / tot;
-        const double lnl = log(tot) + (double)emax * LN2 - log((double)p.K);
-        if (p.lnl && lane == 0) p.lnl[p.out0 + oc] = lnl;
-        if (p.joint || p.compact) {
-            __syncwarp();
-            if (lane < NS) {
+            for (int b = 0; b < NS; ++b) rs += row[c][b];
+            double tot = rs;
 #pragma unroll
-                for (int b = 0; b < NS; ++b) sOut[warp][lane * NS + b] = row[b] * inv;
-            }
-            __syncwarp();
-            if (p.joint) {
-                double* dst = p.joint + (size_t)(p.out0 + oc) * (NS * NS);
-                for (int e = lane; e < NS * NS; e += 32) dst[e] = sOut[warp][e];
-            }
-            if (p.compact) {
-                // SiteResult's scan (recon/SiteResult.java:69-83): maxII, max, entries >= threshold in a-major order
-                double mxp = 0.0, mxii = 0.0;
-                int nk = 0;
-                for (int e = lane; e < NS * NS; e += 32) {
-                    const double v = sOut[warp][e];
-                    mxp = fmax(mxp, v);
-                    if (e / NS == e % NS) mxii = fmax(mxii, v);
-                }
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            const double inv = 1.0 / tot;
+            const double lnl = log(tot) + (double)emax[c] * LN2 - log((double)p.K);
+            if (p.lnl && lane == 0) p.lnl[p.out0 + oc] = lnl;
+            if (p.joint || p.compact) {
+                __syncwarp();
+                if (lane < NS) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    mxp = fmax(mxp, __shfl_xor_sync(0xffffffffu, mxp, o));
-                    mxii = fmax(mxii, __shfl_xor_sync(0xffffffffu, mxii, o));
+                    for (int b = 0; b < NS; ++b) sOut[warp][lane * NS + b] = row[c][b] * inv;
                 }
-                const int cap = p.compact_cap;
-                unsigned char* recb = reinterpret_cast<unsigned char*>(p.compact) + (size_t)(p.out0 + oc) * compact_stride(cap);
-                CompactRec* rec = reinterpret_cast<CompactRec*>(recb);                  // the head is common to every capacity
-                int16_t* pair = reinterpret_cast<int16_t*>(recb + 32);
-                double* prob = reinterpret_cast<double*>(recb + 32 + compact_pairs_bytes(cap));
-                for (int base = 0; base < NS * NS; base += 32) {
-                    const int e = base + lane;
-                    const bool keep = e < NS * NS && sOut[warp][e] >= p.threshold;
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    const int pos = nk + __popc(m & ((1u << lane) - 1));
-                    if (keep && pos < cap) { pair[pos] = (int16_t)e; prob[pos] = sOut[warp][e]; }
-                    nk += __popc(m);
+                __syncwarp();
+                if (p.joint) {
+                    double* dst = p.joint + (size_t)(p.out0 + oc) * (NS * NS);
+                    for (int e = lane; e < NS * NS; e += 32) dst[e] = sOut[warp][e];
                 }
-                if (lane == 0) {
-                    rec->lnl = lnl; rec->max_ii = mxii; rec->max_p = mxp; rec->n_kept = nk;
-                    rec->interesting = (mxii <= 1.0 - p.threshold && mxp >= p.threshold) ? 1 : 0;
+                if (p.compact) {
+                    // SiteResult's scan (recon/SiteResult.java:69-83): maxII, max, entries >= threshold in a-major order
+                    double mxp = 0.0, mxii = 0.0;
+                    int nk = 0;
+                    for (int e = lane; e < NS * NS; e += 32) {
+                        const double v = sOut[warp][e];
+                        mxp = fmax(mxp, v);
+                        if (e / NS == e % NS) mxii = fmax(mxii, v);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        mxp = fmax(mxp, __shfl_xor_sync(0xffffffffu, mxp, o));
+                        mxii = fmax(mxii, __shfl_xor_sync(0xffffffffu, mxii, o));
+                    }
+                    const int cap = p.compact_cap;
+                    unsigned char* recb = reinterpret_cast<unsigned char*>(p.compact) + (size_t)(p.out0 + oc) * compact_stride(cap);
+                    CompactRec* rec = reinterpret_cast<CompactRec*>(recb);                  // the head is common to every capacity
+                    int16_t* pair = reinterpret_cast<int16_t*>(recb + 32);
+                    double* prob = reinterpret_cast<double*>(recb + 32 + compact_pairs_bytes(cap));
+                    for (int base = 0; base < NS * NS; base += 32) {
+                        const int e = base + lane;
+                        const bool keep = e < NS * NS && sOut[warp][e] >= p.threshold;
+                        const unsigned m = __ballot_sync(0xffffffffu, keep);
+                        const int pos = nk + __popc(m & ((1u << lane) - 1));
+                        if (keep && pos < cap) { pair[pos] = (int16_t)e; prob[pos] = sOut[warp][e]; }
+                        nk += __popc(m);
+                    }
+                    if (lane == 0) {
+                        rec->lnl = lnl; rec->max_ii = mxii; rec->max_p = mxp; rec->n_kept = nk;
+                        rec->interesting = (mxii <= 1.0 - p.threshold && mxp >= p.threshold) ? 1 : 0;
+                    }
+                    for (int e = nk + lane; e < compact_pairs_bytes(cap) / 2; e += 32) pair[e] = -1;      // unused slots (and the padding)
+                    for (int e = nk + lane; e < cap; e += 32) prob[e] = 0.0;
                 }
-                for (int e = nk + lane; e < compact_pairs_bytes(cap) / 2; e += 32) pair[e] = -1;      // unused slots (and the padding)
-                for (int e = nk + lane; e < cap; e += 32) prob[e] = 0.0;
+                __syncwarp();                                                           // sOut is reused by the next column
             }
         }
     }

@@ -712,7 +712,8 @@ int run_block_plain(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t 
     r.col_skip = skip;
     r.out0 = out0;
     r.K = c->K;
-    const int64_t blocks = std::min<int64_t>((n + ROOT_WARPS - 1) / ROOT_WARPS, (int64_t)c->n_sm * 8);
+    const int64_t groups = (n + ROOT_COLS - 1) / ROOT_COLS;                 // a warp takes ROOT_COLS columns at a time
+    const int64_t blocks = std::min<int64_t>((groups + ROOT_WARPS - 1) / ROOT_WARPS, (int64_t)c->n_sm * 8);
     prof_begin(c, s, 2, n);
     if (c->K <= ROOT_SMEM_MAX_K) {
         const int psm = c->K * NS * NS * (int)sizeof(double);
