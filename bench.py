@@ -72,7 +72,8 @@ def parse_args():
     ap.add_argument("--columns", type=int, default=0, help="override the config's column count")
     ap.add_argument("--alpha", type=float, default=0.5)
     ap.add_argument("--chunk-cols", type=int, default=0, help="0 = library default")
-    ap.add_argument("--distinct", action="store_true", help="simulate every column (no tiling of a base block)")
+    ap.add_argument("--tiled", action="store_true",
+                    help="fill the alignment by repeating a block of `base` simulated columns instead of simulating every column")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-joint", action="store_true", help="skip the 3 208 B/column end-to-end variant")
@@ -90,7 +91,7 @@ def config_of(a):
 
 def workload_config(a, c, columns_per_gpu, world):
     data = ("the reference's own example alignment" if c.get("kind") == "example" else
-            f"columns simulated down the tree ({'all distinct' if a.distinct else str(min(c['base'], c['columns'])) + ' distinct, tiled'})")
+            f"columns simulated down the tree ({str(min(c['base'], c['columns'])) + ' distinct, tiled' if a.tiled else 'every column its own draw, generated on the GPU before the timed region'})")
     big = columns_per_gpu * c.get("taxa", 19) > 2 ** 28
     return {"workload": f"BASELINE config #{a.config}: {c['label']}, alpha={a.alpha}; {data}",
             "baseline_config": a.config, "taxa": c.get("taxa", 19),
@@ -136,34 +137,20 @@ def make_problem(a, c, seed_shift=0):
     return tree, treeio.flatten_tree(tree), model, rates, base
 
 
-def _sim_block(job):
-    cfg, alpha, n, seed = job
-    from subrecon_b200 import palmodel, synth
-
-    class A:
-        pass
-    a = A()
-    a.alpha = alpha
-    c = dict(CONFIGS[cfg])
-    return synth.simulate_alignment(make_tree(c), make_model(a, c), palmodel.gamma_rates(c["ncat"], alpha), n, seed=seed)
-
-
-def fill_states(a, c, dst, base, rank, world):
-    """dst[taxa][L] <- the base block tiled, or (--distinct) L columns each simulated down the tree (host cores in parallel)."""
+def fill_states(a, c, dst, base, rank, device, tree, model, rates):
+    """dst[taxa][L] <- L columns each simulated down the tree (torch ops on this rank's GPU: data generation, outside every
+    timed region), or (--tiled) the numpy-simulated base block repeated. The table-row gathers of the pruning kernel see
+    what real data would show them only when the columns are distinct (8 192 tiled columns keep the hot rows in L1/L2)."""
     L = dst.shape[1]
-    if not a.distinct or c.get("kind") == "example":
+    if a.tiled or c.get("kind") == "example":
         for c0 in range(0, L, base.shape[1]):
             w = min(base.shape[1], L - c0)
             dst[:, c0:c0 + w] = base[:, :w]
         return
-    import multiprocessing as mp
-    blk = 16384
-    starts = list(range(0, L, blk))
-    jobs = [(a.config, a.alpha, min(blk, L - c0), 1_000_003 * (rank + 1) + c0) for c0 in starts]
-    procs = max(1, min(len(jobs), (os.cpu_count() or 2) // max(1, world)))
-    with mp.get_context("spawn").Pool(procs) as pool:
-        for c0, part in zip(starts, pool.imap(_sim_block, jobs)):
-            dst[:, c0:c0 + part.shape[1]] = part
+    import torch
+    from subrecon_b200 import synth
+    synth.simulate_alignment_torch(tree, model, rates, L, seed=c["aln_seed"] + 7919 * rank, device=device, out=dst)
+    torch.cuda.empty_cache()
 
 
 class ClockSampler(threading.Thread):
@@ -363,7 +350,7 @@ def run_b200(a):
 
     # host (pinned) copies of the step's inputs and outputs
     h_states = native.PinnedArray((N, L), np.uint8)
-    fill_states(a, c, h_states.array, base, rank, world)
+    fill_states(a, c, h_states.array, base, rank, f"cuda:{local}", tree, model, rates)
     h_lnl = native.PinnedArray(L, np.float64)
 
     # ---- value: alignment resident in HBM, results stay in HBM
@@ -491,7 +478,7 @@ def run_b200(a):
                 m.set_tree(flat)
                 ms_states = h_states if world == 1 else native.PinnedArray((N, Lm), np.uint8)
                 if world > 1:
-                    fill_states(a, c, ms_states.array, base, 0, 1)
+                    fill_states(a, c, ms_states.array, base, 0, f"cuda:{local}", tree, model, rates)
                 ms_lnl = native.PinnedArray(Lm, np.float64)
                 ms_comp = native.PinnedArray(Lm, comp_dtype)
                 outm = {"lnl": ms_lnl.array, "compact": ms_comp.array}
@@ -537,7 +524,7 @@ def run_b200(a):
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (same launch size), else null
     traffic, traffic_note = None, None
     try:
-        if a.config == 3 and L == 1_000_000 and not a.distinct:
+        if a.config == 3 and L == 1_000_000:
             prof_json = json.load(open(os.path.join(ROOT, "profiles", "r02_prune_kernel_ncu_full_1Mcols.json")))
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
             traffic = sum(float(prof_json[k]["value"]) * scale[prof_json[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))

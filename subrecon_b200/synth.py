@@ -146,3 +146,53 @@ def simulate_alignment_parallel(tree: Tree, model, rates, n_sites: int, seed: in
         with mp.get_context("fork").Pool(procs) as pool:
             parts = pool.map(_sim_job, jobs)
     return np.concatenate(parts, axis=1)
+
+
+def simulate_alignment_torch(tree: Tree, model, rates, n_sites: int, seed: int, device="cuda", gap_frac=0.01, x_frac=0.001,
+                             block=1 << 17, out=None) -> np.ndarray:
+    """The same generative process as `simulate_alignment` (root state from pi, one rate class per column, a child's state
+    drawn from row `parent state` of P(t_child * rate), `gap_frac + x_frac` of the cells missing), vectorised over columns
+    with torch ops on `device` — plumbing for synthetic DATA only (bench.py wants 10^6..10^7 distinct columns in seconds;
+    the numpy version takes minutes). Different random stream than the numpy version, same distribution
+    (tests/test_host.py::test_torch_simulator_matches_the_numpy_one). Columns come in blocks of `block`, block i seeded with
+    (seed, i): the first columns of a longer run equal a shorter run with the same seed. Returns / fills uint8
+    states[tip][site], tips in node order."""
+    import torch
+    K = len(rates)
+    n_nodes = len(tree.children)
+    tips = [v for v in range(n_nodes) if not tree.children[v]]
+    row_of = {v: i for i, v in enumerate(tips)}
+    if out is None:
+        out = np.empty((len(tips), n_sites), dtype=np.uint8)
+    # cumulative transition rows per (node, rate class): [n_nodes][K*20][20]
+    cdf = np.zeros((n_nodes, K * 20, 20))
+    for v in range(1, n_nodes):
+        for k in range(K):
+            P = transition_matrix(model.Eval, model.Evec, model.Ievc, tree.blen[v] * rates[k])
+            cdf[v, k * 20:(k + 1) * 20] = np.cumsum(P / P.sum(axis=1, keepdims=True), axis=1)
+    cdf_d = torch.from_numpy(cdf).to(device)
+    cdf_pi = torch.from_numpy(np.cumsum(model.pi / model.pi.sum())).to(device)
+    g = torch.Generator(device=device)
+    miss = gap_frac + x_frac
+    for bi, c0 in enumerate(range(0, n_sites, block)):
+        n = min(block, n_sites - c0)
+        g.manual_seed(int(seed) * 1_000_003 + bi)
+        # (always draw a full block so that a ragged last block is a prefix of the full one)
+        cls20 = torch.randint(0, K, (block,), generator=g, device=device)[:n] * 20
+        root = torch.searchsorted(cdf_pi, torch.rand(block, generator=g, device=device, dtype=torch.float64)[:n]).clamp_(max=19)
+        blk = torch.empty((len(tips), n), dtype=torch.uint8, device=device)
+        stack = [(0, root)]
+        while stack:
+            v, sv = stack.pop()
+            if not tree.children[v]:
+                cell = sv.to(torch.uint8)
+                if miss:
+                    cell = torch.where(torch.rand(block, generator=g, device=device)[:n] < miss, torch.full_like(cell, MISSING), cell)
+                blk[row_of[v]] = cell
+                continue
+            for c in tree.children[v]:
+                rows = cdf_d[c][cls20 + sv]                                          # [n, 20]
+                u = torch.rand(block, generator=g, device=device, dtype=torch.float64)[:n]
+                stack.append((c, (rows < u[:, None]).sum(dim=1).clamp_(max=19)))
+        out[:, c0:c0 + n] = blk.cpu().numpy()
+    return out

@@ -142,3 +142,28 @@ def test_state_golden_regenerates_from_the_jar():
     import make_states_golden
     cls, states, stubbed = make_states_golden.jar_states()
     assert cls == "pal/datatype/SpecificAminoAcids" and stubbed == [] and states == jar_state_lut()[1]
+
+
+def test_torch_simulator_matches_the_numpy_one():
+    """bench.py fills its alignments with `simulate_alignment_torch` (every column distinct, seconds on a GPU); the parity
+    tests use the numpy simulator. Same generative model: compare what the kernels' behaviour depends on — state
+    frequencies, missing cells, identity between tips, the share of constant columns — and the prefix property."""
+    tree = synth.yule_tree(40, seed=7)
+    m, r = palmodel.host_model("wag"), palmodel.gamma_rates(4, 0.5)
+    n = 30_000
+    a = synth.simulate_alignment(tree, m, r, n, seed=1)
+    b = synth.simulate_alignment_torch(tree, m, r, n, seed=2, device="cpu", block=8192)
+    assert a.shape == b.shape and b.dtype == np.uint8 and set(np.unique(b)) <= set(range(20)) | {treeio.MISSING}
+    assert abs((a == 255).mean() - (b == 255).mean()) < 2e-3
+    fa = np.bincount(a[a < 20], minlength=20) / np.count_nonzero(a < 20)
+    fb = np.bincount(b[b < 20], minlength=20) / np.count_nonzero(b < 20)
+    assert np.abs(fa - fb).max() < 0.01
+    for i, j in ((0, 1), (3, 30), (10, 39)):
+        assert abs(np.mean(a[i] == a[j]) - np.mean(b[i] == b[j])) < 0.015
+
+    def constant(x):
+        y = np.where(x == 255, x[0][None, :], x)
+        return np.mean((y == y[0][None, :]).all(axis=0))
+    assert abs(constant(a) - constant(b)) < 0.02
+    short = synth.simulate_alignment_torch(tree, m, r, 10_000, seed=2, device="cpu", block=8192)
+    assert np.array_equal(short, b[:, :10_000])                       # a shorter run is a prefix of a longer one

@@ -20,7 +20,7 @@ ap.add_argument("--taxa", type=int, default=1000)
 ap.add_argument("--tree", default="yule")
 ap.add_argument("--ncat", type=int, default=4)
 ap.add_argument("--uniform", action="store_true", help="uniform random states instead of simulated columns")
-ap.add_argument("--distinct", action="store_true", help="simulate every column down the tree (host cores in parallel) instead of tiling 4096")
+ap.add_argument("--distinct", action="store_true", help="simulate every column down the tree (on the GPU, like bench.py) instead of tiling 4096")
 ap.add_argument("--model", default="wag")
 ap.add_argument("--const", action="store_true", help="every tip in state 0 (no shared-memory bank conflicts in the tip gathers)")
 a = ap.parse_args()
@@ -37,7 +37,7 @@ elif a.distinct:
 else:
     base = synth.simulate_alignment(tree, model, rates, 4096, seed=103)
 if base is None:
-    states = synth.simulate_alignment_parallel(tree, model, rates, a.cols, seed=103)
+    states = synth.simulate_alignment_torch(tree, model, rates, a.cols, seed=103, device="cuda")      # what bench.py feeds the path by default
 else:
     states = np.tile(base, (1, (a.cols + 4095) // 4096))[:, :a.cols]
 ctx = native.Context(0)
