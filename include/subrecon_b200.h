@@ -154,7 +154,9 @@ void sr_host_free(void *p);
  * "strict_root" (0/1, default 0: reject, with SR_ERR_UNSUPPORTED from sr_set_tree / sr_set_rates, a tree whose root has a
  * tip as child when K > 1 — the reference throws on every column of such input, utils/Utils.java:56-70; off = return the
  * well-defined limit), "compress_patterns" (0/1: compute each distinct column pattern of a batch once and copy the result
- * to its duplicates; off by default), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage),
+ * to its duplicates — patterns are found by 128-bit hashes and every column is then compared byte for byte with its
+ * pattern's representative, a block with a hash collision is computed the plain way; off by default; 2 = test mode with a
+ * deliberately weak hash), "chunk_cols" / "stream_chunk_cols" (columns per launch / per pipeline stage),
  * "stream_taper" (0/1: short pipeline chunks at both ends of a streamed run, on by default), "input_chars" (0/1:
  * alignment bytes are residue letters, see sr_set_alignment), "cherry_tables" (0/1, default 1: tabulate every cherry's
  * contribution per state pair once per rate class and gather it instead of contracting it per column) with

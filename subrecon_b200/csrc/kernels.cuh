@@ -328,18 +328,19 @@ __global__ void __launch_bounds__(256) encode_chars_kernel(uint4* __restrict__ v
 // ------------------------------------------------------------------------------------------- column patterns
 // Identical alignment columns have identical results, so a batch can be reduced to its distinct column patterns
 // (the reference recomputes every column, SubRecon.java:112-116). A pattern is identified by a 128-bit
-// hash of its state codes; equal hashes are treated as equal columns.
+// hash of its state codes; columns with equal hashes are then compared byte for byte (verify_patterns_kernel).
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {          // murmur3 finaliser
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
 __global__ void __launch_bounds__(256) hash_columns_kernel(const uint8_t* __restrict__ states, int64_t pitch, int n_taxa,
                                                            int64_t n, uint64_t* __restrict__ h1, uint64_t* __restrict__ h2,
-                                                           uint32_t* __restrict__ idx) {
+                                                           uint32_t* __restrict__ idx, int hashed_taxa) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     uint64_t a = 0x9e3779b97f4a7c15ULL, b = 0xc2b2ae3d27d4eb4fULL;
-    for (int t = 0; t < n_taxa; ++t) {                           // adjacent threads read adjacent bytes of one row
+    // (hashed_taxa < n_taxa only in the test mode that provokes collisions, option "compress_patterns" = 2)
+    for (int t = 0; t < hashed_taxa; ++t) {                      // adjacent threads read adjacent bytes of one row
         const uint64_t v = states[(int64_t)t * pitch + c];
         a = (a ^ v) * 0x100000001b3ULL;
         b = mix64(b + v + 0x632be59bd9b4e019ULL * (uint64_t)(t + 1));
@@ -371,6 +372,20 @@ __global__ void __launch_bounds__(256) gather_patterns_kernel(const uint8_t* __r
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
     if (u < out_pitch && t < n_taxa) out[(int64_t)t * out_pitch + u] = (u < n_uniq) ? states[(int64_t)t * pitch + rep[u]] : (uint8_t)NS;
+}
+// Equal hashes are only a claim: every column is compared byte for byte with the representative of the pattern it was
+// mapped to (the gathered pattern matrix is small and stays in L2; the alignment block is read once, coalesced). Any
+// difference raises the flag and the caller recomputes the block the plain way.
+__global__ void __launch_bounds__(256) verify_patterns_kernel(const uint8_t* __restrict__ states, int64_t pitch, int n_taxa, int64_t n,
+                                                              const uint32_t* __restrict__ map, const uint8_t* __restrict__ pat,
+                                                              int64_t pat_pitch, int* __restrict__ mismatch) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const uint32_t u = map[c];
+    const int t0 = blockIdx.y * 32, t1 = min(n_taxa, t0 + 32);
+    bool bad = false;
+    for (int t = t0; t < t1; ++t) bad |= states[(int64_t)t * pitch + c] != pat[(int64_t)t * pat_pitch + u];
+    if (bad) atomicOr(mismatch, 1);
 }
 // results of the distinct patterns back to every original column: one warp per column
 __global__ void __launch_bounds__(256) scatter_patterns_kernel(const uint32_t* __restrict__ map, int64_t n, int64_t out0,

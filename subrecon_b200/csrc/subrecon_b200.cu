@@ -107,7 +107,7 @@ struct sr_ctx {
 
     // device state
     DevBuf d_model, d_rates, d_crec, d_prec, d_cgathers, d_cidx, d_slotkind, d_slotoff, d_slotblen, d_pstream, d_proot, d_states, d_rootpart, d_rootexp, d_spill;
-    DevBuf d_pat_keys[2], d_pat_idx[2], d_pat_h2, d_pat_head, d_pat_uid, d_pat_rep, d_pat_map, d_pat_tmp, d_pat_states, d_pat_lnl, d_pat_joint, d_pat_compact;
+    DevBuf d_pat_keys[2], d_pat_idx[2], d_pat_h2, d_pat_head, d_pat_uid, d_pat_rep, d_pat_map, d_pat_tmp, d_pat_states, d_pat_lnl, d_pat_joint, d_pat_compact, d_pat_flag;
     int64_t last_unique = 0, last_total = 0;
     DevBuf d_chunk_states[3], d_chunk_lnl[3], d_chunk_joint[3], d_chunk_compact[3], d_peak;   // pipeline buffers (sr_run: 2, streamed: 3)
     int32_t aln_taxa = 0;
@@ -746,7 +746,7 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
     CUDA_TRY(c, c->d_pat_map.reserve(sizeof(uint32_t) * n));
     const unsigned nb = (unsigned)((n + 255) / 256);
     hash_columns_kernel<<<nb, 256, 0, s>>>(base, pitch, n_taxa, n, c->d_pat_keys[0].as<uint64_t>(), c->d_pat_h2.as<uint64_t>(),
-                                           c->d_pat_idx[0].as<uint32_t>());
+                                           c->d_pat_idx[0].as<uint32_t>(), c->compress == 2 ? std::min(n_taxa, 2) : n_taxa);
     size_t tmp_sort = 0, tmp_scan = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, c->d_pat_keys[0].as<uint64_t>(), c->d_pat_keys[1].as<uint64_t>(),
                                     c->d_pat_idx[0].as<uint32_t>(), c->d_pat_idx[1].as<uint32_t>(), (int)n, 0, 64, s);
@@ -770,6 +770,11 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
     CUDA_TRY(c, c->d_pat_states.reserve((size_t)up * n_taxa + 512));
     gather_patterns_kernel<<<dim3((unsigned)((up + 255) / 256), n_taxa), 256, 0, s>>>(base, pitch, n_taxa, c->d_pat_rep.as<uint32_t>(), n_uniq,
                                                                                    c->d_pat_states.as<uint8_t>(), up);
+    // the hashes' verdict is checked against the bytes; the flag is read after the block's kernels have been enqueued
+    CUDA_TRY(c, c->d_pat_flag.reserve(sizeof(int)));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_pat_flag.p, 0, sizeof(int), s));
+    verify_patterns_kernel<<<dim3(nb, (unsigned)((n_taxa + 31) / 32)), 256, 0, s>>>(base, pitch, n_taxa, n, c->d_pat_map.as<uint32_t>(),
+                                                                                  c->d_pat_states.as<uint8_t>(), up, c->d_pat_flag.as<int>());
     CUDA_TRY(c, c->d_pat_lnl.reserve(sizeof(double) * n_uniq));
     if (d_joint) CUDA_TRY(c, c->d_pat_joint.reserve(sizeof(double) * 400 * (size_t)n_uniq));
     if (d_compact) CUDA_TRY(c, c->d_pat_compact.reserve((size_t)compact_stride(c->compact_cap) * (size_t)n_uniq));
@@ -781,6 +786,13 @@ int run_block(sr_ctx* c, cudaStream_t s, const uint8_t* d_states, int64_t pitch,
                                                          d_compact ? c->d_pat_compact.as<uint64_t>() : nullptr, d_lnl, d_joint,
                                                          reinterpret_cast<uint64_t*>(d_compact), compact_stride(c->compact_cap) / 8);
     CUDA_TRY(c, cudaGetLastError());
+    int mismatch = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&mismatch, c->d_pat_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (mismatch) {          // two different columns shared a 128-bit hash: this block is computed column by column instead
+        c->last_unique += n - n_uniq;
+        return run_block_plain(c, s, d_states, pitch, col_begin, n, d_lnl, d_joint, d_compact, threshold, out0);
+    }
     return SR_OK;
 }
 
@@ -1231,7 +1243,8 @@ static int sr_set_option_impl(sr_ctx* c, const char* name, int64_t value) {
         if (value < 256) return fail(c, SR_ERR_ARG, "chunk_cols must be >= 256");
         c->chunk_cols = (value + 255) / 256 * 256;
     } else if (k == "compress_patterns") {
-        c->compress = value != 0;
+        if (value < 0 || value > 2) return fail(c, SR_ERR_ARG, "compress_patterns must be 0, 1 or 2");
+        c->compress = (int)value;                      // 2 = test mode: hash only the first two taxa, so that hashes collide
         c->last_unique = c->last_total = 0;
     } else if (k == "cherry_tables") {
         c->cherry_tables = value != 0;

@@ -385,6 +385,17 @@ def test_column_pattern_compression(ctx, example_problem):
         assert np.array_equal(r["lnl"], np.tile(plain["lnl"], 300))
         st = ctx.run_streamed(big)
         assert np.array_equal(st["lnl"], r["lnl"]) and np.array_equal(st["joint"][:130], plain["joint"])
+        # Equal hashes are verified against the bytes. Mode 2 hashes only the first two taxa, so different columns collide:
+        # the byte compare must notice and the block is recomputed column by column — same bits, nothing saved.
+        ctx.set_option("compress_patterns", 2)
+        ctx.set_alignment(p.states)
+        ctx.profile(reset=True)
+        coll = ctx.run(want_joint=True, want_compact=True, threshold=0.3)
+        prof = ctx.profile(reset=True)
+        assert len({bytes(c) for c in p.states[:2].T}) < 51                      # the weak hash really merges distinct columns
+        assert prof["columns_in"] == 130 and prof["columns_unique"] == 130
+        assert np.array_equal(coll["lnl"], plain["lnl"]) and np.array_equal(coll["joint"], plain["joint"])
+        assert coll["compact"].tobytes() == plain["compact"].tobytes()
     finally:
         ctx.set_option("compress_patterns", 0)
 
