@@ -91,7 +91,7 @@ def config_of(a):
 
 def workload_config(a, c, columns_per_gpu, world):
     data = ("the reference's own example alignment" if c.get("kind") == "example" else
-            f"columns simulated down the tree ({str(min(c['base'], c['columns'])) + ' distinct, tiled' if a.tiled else 'every column its own draw, generated on the GPU before the timed region'})")
+            f"columns simulated down the tree ({str(min(c['base'], c['columns'])) + ' distinct, tiled' if a.tiled else 'every column its own draw'})")
     big = columns_per_gpu * c.get("taxa", 19) > 2 ** 28
     return {"workload": f"BASELINE config #{a.config}: {c['label']}, alpha={a.alpha}; {data}",
             "baseline_config": a.config, "taxa": c.get("taxa", 19),
