@@ -1167,11 +1167,14 @@ static int sr_run_streamed_impl(sr_ctx* c, int32_t n_taxa, int64_t n_sites, cons
             // page-locked bounce buffer on the host thread instead; the DMA then runs from pinned memory like any other.
             const size_t need = (size_t)mmax * n_taxa;                   // sized for a full chunk once, not per ramp step
             if (c->h_bounce_cap[b] < need) {
-                if (c->h_bounce[b]) { if (ci >= NB) cudaEventSynchronize(up_ev[b]); cudaFreeHost(c->h_bounce[b]); c->h_bounce[b] = nullptr; c->h_bounce_cap[b] = 0; }
+                if (c->h_bounce[b]) {
+                    if (ci >= NB) CUDA_STEP(c, rc, cudaEventSynchronize(up_ev[b]));
+                    cudaFreeHost(c->h_bounce[b]); c->h_bounce[b] = nullptr; c->h_bounce_cap[b] = 0;
+                }
                 if (cudaMallocHost(&c->h_bounce[b], need) != cudaSuccess) { cudaGetLastError(); rc = fail(c, SR_ERR_OOM, "cannot allocate the pinned staging buffer"); break; }
                 c->h_bounce_cap[b] = need;
             } else if (ci >= NB) {
-                cudaEventSynchronize(up_ev[b]);                          // the DMA out of this bounce buffer (chunk ci-NB) is done
+                CUDA_STEP(c, rc, cudaEventSynchronize(up_ev[b]));        // the DMA out of this bounce buffer (chunk ci-NB) is done
             }
             uint8_t* hb = static_cast<uint8_t*>(c->h_bounce[b]);
             for (int t = 0; t < n_taxa; ++t) memcpy(hb + (size_t)t * m, src + (size_t)t * pitch, (size_t)m);
