@@ -78,6 +78,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-joint", action="store_true", help="skip the 3 208 B/column end-to-end variant")
     ap.add_argument("--no-single-process", action="store_true", help="skip the one-process-N-GPUs end-to-end variant")
+    ap.add_argument("--single-process-devices", type=int, default=0,
+                    help="without torchrun: let the one-process leg (sr_multi_*) drive this many GPUs, the config's columns on each "
+                         "(no other rank's process shares the GPUs, as under a single JVM)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -471,13 +474,17 @@ def run_b200(a):
             dist.barrier(group=cpu_group)
         if rank == 0:
             try:
-                Lm = total_columns
-                m = native.MultiContext(list(range(world)))
+                n_multi = world
+                if world == 1 and a.single_process_devices > 1:
+                    n_multi = min(a.single_process_devices, torch.cuda.device_count())
+                Lm = total_columns if n_multi == world else L * n_multi
+                m = native.MultiContext(list(range(n_multi)))
                 m.set_model(model.Eval, model.Evec, model.Ievc, model.pi)
                 m.set_rates(rates)
                 m.set_tree(flat)
-                ms_states = h_states if world == 1 else native.PinnedArray((N, Lm), np.uint8)
-                if world > 1:
+                own_states = Lm != L
+                ms_states = native.PinnedArray((N, Lm), np.uint8) if own_states else h_states
+                if own_states:
                     fill_states(a, c, ms_states.array, base, 0, f"cuda:{local}", tree, model, rates)
                 ms_lnl = native.PinnedArray(Lm, np.float64)
                 ms_comp = native.PinnedArray(Lm, comp_dtype)
@@ -499,7 +506,7 @@ def run_b200(a):
                                       "library, contiguous column blocks, compact records land in place",
                               "first_records_identical_to_per_process_run": same}
                 m.close()
-                for h in (ms_lnl, ms_comp) + ((ms_states,) if world > 1 else ()):
+                for h in (ms_lnl, ms_comp) + ((ms_states,) if own_states else ()):
                     h.free()
             except Exception as exc:                        # never lose the main line over the extra leg
                 e2e_single = {"error": str(exc)}
