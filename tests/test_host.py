@@ -167,3 +167,24 @@ def test_torch_simulator_matches_the_numpy_one():
     assert abs(constant(a) - constant(b)) < 0.02
     short = synth.simulate_alignment_torch(tree, m, r, 10_000, seed=2, device="cpu", block=8192)
     assert np.array_equal(short, b[:, :10_000])                       # a shorter run is a prefix of a longer one
+
+
+def test_bench_clock_sampler_windows():
+    """bench.py reports clocks / power / throttle reasons for the window `value` was timed over (and for the whole run): the
+    windowing must pick the right samples, fall back to the nearest one for a region shorter than the sampling period,
+    and name any throttle reason seen inside the window."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    s = bench.ClockSampler(0)
+    s.nvml = None                                                   # no NVML / GPU here: feed samples by hand
+    off = [False] * 4
+    s.samples = [(0.0, 1965.0, 1965.0, 300.0, off), (1.0, 1965.0, 1965.0, 640.0, off), (2.0, 1800.0, 1965.0, 990.0, [False, False, False, True]),
+                 (3.0, 1965.0, 1965.0, 310.0, off)]
+    w = s.window(0.5, 1.5)
+    assert w["samples"] == 1 and w["sm_mhz"] == 1965.0 and w["reasons"] == [] and w["power_w_max"] == 640.0
+    w = s.window(0.5, 2.5)
+    assert w["samples"] == 2 and w["sm_min_mhz"] == 1800.0 and w["reasons"] == ["sw_power_cap"] and w["sm_max_mhz"] == 1965.0
+    w = s.window(1.2, 1.3)                                          # shorter than the period: the nearest sample stands in
+    assert w["samples"] == 1 and w["power_w_max"] == 640.0
+    assert s.window(None, None)["samples"] == 4
+    assert bench.ClockSampler.NAMES == ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
