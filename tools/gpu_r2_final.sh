@@ -7,7 +7,7 @@ O=gpurun_out
 timeout -s KILL 1800 python -m pytest tests -m gpu -x -q > $O/r02_pytest_gpu.log 2>&1; tail -3 $O/r02_pytest_gpu.log
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 timeout -s KILL 600 $B > $O/r02_bench_line_same_command.json 2> $O/r02_bench_line_same_command.err && \
-timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r02_launches_bench.csv $B > $O/r02_bench_under_ncu.log 2>&1
+timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:prune_kernel|root_kernel|cherry_kernel|pbuild_kernel|clade_index_kernel|sanitize_kernel|encode_chars_kernel|dmma_peak_kernel" -c 600 --csv --log-file $O/r02_launches_bench.csv $B > $O/r02_bench_under_ncu.log 2>&1
 cut -c1-200 $O/r02_bench_line_same_command.json
 P="python tools/prune_probe.py --cols 1000000 --reps 2"
 timeout -s KILL 300 $P --distinct > $O/r02_probe_1m_distinct.log 2>&1 && \
